@@ -1,0 +1,374 @@
+// K7: index / degree work on the device (CSR build, transpose, row extraction, histograms),
+// the synthetic R-MAT generator, and the two small dense row kernels of the affinity path.
+// Integer outputs are bit-exact with the CPU restatement (sorting is by exact integer keys).
+// cub::DeviceRadixSort (shipped with the CUDA toolkit) does the one-off sorts; nothing here
+// is on the per-step hot path.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace ggad {
+
+// ---------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------
+__global__ void rowptr_from_sorted_keys(const uint64_t* __restrict__ keys, int64_t n, int64_t n_rows,
+                                        int64_t* __restrict__ rowptr) {
+  const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r > n_rows) return;
+  const uint64_t target = uint64_t(r) << 32;  // first key with row >= r
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (keys[mid] < target) lo = mid + 1;
+    else hi = mid;
+  }
+  rowptr[r] = lo;
+}
+
+__global__ void low32_of_keys(const uint64_t* __restrict__ keys, int64_t n, int32_t* __restrict__ out) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = int32_t(uint32_t(keys[i] & 0xffffffffull));
+}
+
+__global__ void transpose_keys(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n_rows,
+                               int64_t nnz, uint64_t* __restrict__ keys, int64_t* __restrict__ idx) {
+  const int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  int64_t lo = 0, hi = n_rows;  // row r with rowptr[r] <= e < rowptr[r+1]
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (rowptr[mid + 1] <= e) lo = mid + 1;
+    else hi = mid;
+  }
+  keys[e] = (uint64_t(uint32_t(col[e])) << 32) | uint64_t(uint32_t(lo));
+  if (idx) idx[e] = e;
+}
+
+__global__ void gather_vals(const float* __restrict__ val, const int64_t* __restrict__ perm, int64_t n,
+                            float* __restrict__ out) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = val[perm[i]];
+}
+
+__global__ void extract_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                    const float* __restrict__ val, const int32_t* __restrict__ rows, int64_t n_sel,
+                                    const int64_t* __restrict__ sub_rowptr, int32_t* __restrict__ sub_col,
+                                    float* __restrict__ sub_val) {
+  const int64_t w = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;  // one warp per selected row
+  const int lane = threadIdx.x & 31;
+  if (w >= n_sel) return;
+  const int64_t r = rows[w];
+  const int64_t s = rowptr[r], n = rowptr[r + 1] - s, o = sub_rowptr[w];
+  for (int64_t t = lane; t < n; t += 32) {
+    sub_col[o + t] = col[s + t];
+    if (val) sub_val[o + t] = val[s + t];
+  }
+}
+
+__global__ void col_hist_kernel(const int32_t* __restrict__ col, int64_t nnz, int32_t* __restrict__ counts) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < nnz; e += stride) atomicAdd(counts + col[e], 1);
+}
+
+// ---- dense per-row helpers of the affinity path (warp per row) ----
+__global__ void row_inv_norm_kernel(const float* __restrict__ x, int64_t ldx, int64_t n_rows, int d,
+                                    float* __restrict__ inv_norm, float* __restrict__ sumsq) {
+  const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n_rows) return;
+  const float4* p = reinterpret_cast<const float4*>(x + r * ldx);
+  float ss = 0.f;
+  for (int c = lane; c < (d >> 2); c += 32) {
+    const float4 v = __ldg(p + c);
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  if (lane == 0) {
+    if (sumsq) sumsq[r] = ss;
+    const float nrm = sqrtf(ss);
+    inv_norm[r] = nrm > 0.f ? 1.f / nrm : 0.f;  // pow(norm,-1) with inf -> 0 (run.py:177-179)
+  }
+}
+
+__global__ void normalize_backward_kernel(const float* __restrict__ e, int64_t lde, const float* __restrict__ inv_norm,
+                                          float* __restrict__ g, int64_t ldg, int64_t n_rows, int d) {
+  const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n_rows) return;
+  const float inv = __ldg(inv_norm + r);
+  const float4* pe = reinterpret_cast<const float4*>(e + r * lde);
+  float4* pg = reinterpret_cast<float4*>(g + r * ldg);
+  float dt = 0.f;
+  for (int c = lane; c < (d >> 2); c += 32) {
+    const float4 a = __ldg(pe + c), b = pg[c];
+    dt += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) dt += __shfl_xor_sync(0xffffffffu, dt, off);
+  const float s = dt * inv * inv;  // <e^, g> * inv  with e^ = e * inv
+  for (int c = lane; c < (d >> 2); c += 32) {
+    const float4 a = __ldg(pe + c);
+    float4 b = pg[c];
+    b.x = (b.x - a.x * s) * inv;
+    b.y = (b.y - a.y * s) * inv;
+    b.z = (b.z - a.z * s) * inv;
+    b.w = (b.w - a.w * s) * inv;
+    pg[c] = b;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// R-MAT generator
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t& s) {
+  uint64_t z = (s += 0x9e3779b97f4a7c15ull);
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+
+struct RmatParams {
+  int64_t n_edges, n_local;
+  int32_t shard_bits, shard, local_bits;
+  uint64_t seed;
+  uint32_t ta, tab, tabc;  // 16-bit thresholds for (a), (a+b), (a+b+c)
+  uint32_t t0, t1;         // P(col bit = 0 | row bit = 0), P(col bit = 0 | row bit = 1)
+  int64_t filter_lo, filter_hi;
+};
+
+__global__ void rmat_kernel(RmatParams p, uint64_t* __restrict__ keys, unsigned long long* __restrict__ counter) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < p.n_edges; e += stride) {
+    uint64_t st = p.seed * 0xd1342543de82ef95ull + uint64_t(p.shard) * 0x2545f4914f6cdd1dull + uint64_t(e);
+    splitmix64(st);
+    // source shard: row bits fixed by `shard`, column bits drawn from the conditional
+    int64_t src_shard = 0;
+    uint64_t bits = splitmix64(st);
+    for (int l = p.shard_bits - 1; l >= 0; --l) {
+      const uint32_t u = uint32_t(bits & 0xffffu);
+      bits >>= 16;
+      const int rbit = (p.shard >> l) & 1;
+      const int cbit = u < (rbit ? p.t1 : p.t0) ? 0 : 1;
+      src_shard = (src_shard << 1) | cbit;
+    }
+    int64_t dl = 0, sl = 0;
+    for (int attempt = 0; attempt < 32; ++attempt) {
+      dl = 0;
+      sl = 0;
+      int have = 0;
+      for (int l = 0; l < p.local_bits; ++l) {
+        if (have == 0) {
+          bits = splitmix64(st);
+          have = 4;
+        }
+        const uint32_t u = uint32_t(bits & 0xffffu);
+        bits >>= 16;
+        --have;
+        const int q = u < p.ta ? 0 : (u < p.tab ? 1 : (u < p.tabc ? 2 : 3));  // 0:a 1:b 2:c 3:d
+        dl = (dl << 1) | (q >> 1);
+        sl = (sl << 1) | (q & 1);
+      }
+      if (dl < p.n_local && sl < p.n_local) break;
+      if (attempt == 31) {
+        dl %= p.n_local;
+        sl %= p.n_local;
+      }
+    }
+    const int64_t dst = int64_t(p.shard) * p.n_local + dl;
+    const int64_t src = src_shard * p.n_local + sl;
+    if (p.filter_lo < p.filter_hi) {
+      if (src >= p.filter_lo && src < p.filter_hi) {
+        const unsigned long long pos = atomicAdd(counter, 1ull);
+        keys[pos] = (uint64_t(src) << 32) | uint64_t(dst);
+      }
+    } else {
+      keys[e] = (uint64_t(dst) << 32) | uint64_t(src);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host implementations
+// ---------------------------------------------------------------------------
+static inline unsigned blocks_for(int64_t n, int threads = 256) { return (unsigned)((n + threads - 1) / threads); }
+
+static int bits_for(int64_t n) {
+  int b = 0;
+  while ((int64_t(1) << b) < n) ++b;
+  return b < 1 ? 1 : b;
+}
+
+int coo_keys_to_csr_impl(uint64_t* keys, int64_t n, int64_t n_rows, int64_t* rowptr, int32_t* col, cudaStream_t st) {
+  GGAD_REQUIRE(n >= 0 && n_rows >= 0 && rowptr && (n == 0 || (keys && col)), GGAD_ERR_INVALID, "coo_keys_to_csr: bad arguments");
+  if (n > 0) {
+    uint64_t* alt = nullptr;
+    GGAD_CUDA_OK(cudaMallocAsync(&alt, size_t(n) * 8, st));
+    cub::DoubleBuffer<uint64_t> db(keys, alt);
+    size_t tmp_bytes = 0;
+    const int end_bit = 32 + bits_for(n_rows);
+    GGAD_CUDA_OK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, db, n, 0, end_bit, st));
+    void* tmp = nullptr;
+    GGAD_CUDA_OK(cudaMallocAsync(&tmp, tmp_bytes, st));
+    GGAD_CUDA_OK(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, db, n, 0, end_bit, st));
+    if (db.Current() != keys) GGAD_CUDA_OK(cudaMemcpyAsync(keys, db.Current(), size_t(n) * 8, cudaMemcpyDeviceToDevice, st));
+    GGAD_CUDA_OK(cudaFreeAsync(tmp, st));
+    GGAD_CUDA_OK(cudaFreeAsync(alt, st));
+    low32_of_keys<<<blocks_for(n), 256, 0, st>>>(keys, n, col);
+    GGAD_CUDA_OK(cudaGetLastError());
+    count_launch(1);
+  }
+  rowptr_from_sorted_keys<<<blocks_for(n_rows + 1), 256, 0, st>>>(keys, n, n_rows, rowptr);
+  GGAD_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return GGAD_OK;
+}
+
+int csr_transpose_impl(const int64_t* rowptr, const int32_t* col, const float* val, int64_t n_rows, int64_t n_cols,
+                       int64_t nnz, int64_t* rowptrT, int32_t* colT, float* valT, int64_t* perm, cudaStream_t st) {
+  GGAD_REQUIRE(rowptr && rowptrT && n_rows >= 0 && n_cols >= 0 && nnz >= 0, GGAD_ERR_INVALID, "csr_transpose: bad arguments");
+  GGAD_REQUIRE(nnz == 0 || (col && colT), GGAD_ERR_INVALID, "csr_transpose: col/colT required");
+  GGAD_REQUIRE(!val || valT, GGAD_ERR_INVALID, "csr_transpose: valT required when val is given");
+  uint64_t *k0 = nullptr, *k1 = nullptr;
+  int64_t *i0 = nullptr, *i1 = nullptr;
+  const bool need_idx = (val != nullptr) || (perm != nullptr);
+  if (nnz > 0) {
+    GGAD_CUDA_OK(cudaMallocAsync(&k0, size_t(nnz) * 8, st));
+    GGAD_CUDA_OK(cudaMallocAsync(&k1, size_t(nnz) * 8, st));
+    if (need_idx) {
+      GGAD_CUDA_OK(cudaMallocAsync(&i0, size_t(nnz) * 8, st));
+      GGAD_CUDA_OK(cudaMallocAsync(&i1, size_t(nnz) * 8, st));
+    }
+    transpose_keys<<<blocks_for(nnz), 256, 0, st>>>(rowptr, col, n_rows, nnz, k0, i0);
+    GGAD_CUDA_OK(cudaGetLastError());
+    count_launch(1);
+    cub::DoubleBuffer<uint64_t> dk(k0, k1);
+    size_t tmp_bytes = 0;
+    void* tmp = nullptr;
+    // keys are (col, row) with rows already ascending inside each source row; a stable sort on the
+    // col bits alone would do, but sorting the full key keeps the result independent of input order.
+    const int end_bit = 32 + bits_for(n_cols);
+    if (need_idx) {
+      cub::DoubleBuffer<int64_t> di(i0, i1);
+      GGAD_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, di, nnz, 0, end_bit, st));
+      GGAD_CUDA_OK(cudaMallocAsync(&tmp, tmp_bytes, st));
+      GGAD_CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, di, nnz, 0, end_bit, st));
+      if (val) {
+        gather_vals<<<blocks_for(nnz), 256, 0, st>>>(val, di.Current(), nnz, valT);
+        GGAD_CUDA_OK(cudaGetLastError());
+        count_launch(1);
+      }
+      if (perm) GGAD_CUDA_OK(cudaMemcpyAsync(perm, di.Current(), size_t(nnz) * 8, cudaMemcpyDeviceToDevice, st));
+    } else {
+      GGAD_CUDA_OK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, dk, nnz, 0, end_bit, st));
+      GGAD_CUDA_OK(cudaMallocAsync(&tmp, tmp_bytes, st));
+      GGAD_CUDA_OK(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, dk, nnz, 0, end_bit, st));
+    }
+    low32_of_keys<<<blocks_for(nnz), 256, 0, st>>>(dk.Current(), nnz, colT);
+    GGAD_CUDA_OK(cudaGetLastError());
+    rowptr_from_sorted_keys<<<blocks_for(n_cols + 1), 256, 0, st>>>(dk.Current(), nnz, n_cols, rowptrT);
+    GGAD_CUDA_OK(cudaGetLastError());
+    count_launch(2);
+    GGAD_CUDA_OK(cudaFreeAsync(tmp, st));
+    GGAD_CUDA_OK(cudaFreeAsync(k0, st));
+    GGAD_CUDA_OK(cudaFreeAsync(k1, st));
+    if (need_idx) {
+      GGAD_CUDA_OK(cudaFreeAsync(i0, st));
+      GGAD_CUDA_OK(cudaFreeAsync(i1, st));
+    }
+  } else {
+    GGAD_CUDA_OK(cudaMemsetAsync(rowptrT, 0, size_t(n_cols + 1) * 8, st));
+  }
+  return GGAD_OK;
+}
+
+int csr_extract_rows_impl(const int64_t* rowptr, const int32_t* col, const float* val, const int32_t* rows, int64_t n_sel,
+                          const int64_t* sub_rowptr, int32_t* sub_col, float* sub_val, cudaStream_t st) {
+  GGAD_REQUIRE(rowptr && rows && sub_rowptr && n_sel >= 0, GGAD_ERR_INVALID, "csr_extract_rows: bad arguments");
+  GGAD_REQUIRE(!val || sub_val, GGAD_ERR_INVALID, "csr_extract_rows: sub_val required when val is given");
+  if (n_sel == 0) return GGAD_OK;
+  extract_rows_kernel<<<blocks_for(n_sel * 32), 256, 0, st>>>(rowptr, col, val, rows, n_sel, sub_rowptr, sub_col, sub_val);
+  GGAD_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return GGAD_OK;
+}
+
+int col_histogram_impl(const int32_t* col, int64_t nnz, int32_t* counts, int64_t n_cols, cudaStream_t st) {
+  GGAD_REQUIRE(counts && n_cols >= 0 && nnz >= 0 && (nnz == 0 || col), GGAD_ERR_INVALID, "col_histogram: bad arguments");
+  GGAD_CUDA_OK(cudaMemsetAsync(counts, 0, size_t(n_cols) * 4, st));
+  if (nnz == 0) return GGAD_OK;
+  unsigned blocks = blocks_for(nnz);
+  if (blocks > 148u * 32u) blocks = 148u * 32u;
+  col_hist_kernel<<<blocks, 256, 0, st>>>(col, nnz, counts);
+  GGAD_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return GGAD_OK;
+}
+
+int row_inv_norm_impl(const float* x, int64_t ldx, int64_t n_rows, int32_t d, float* inv_norm, float* sumsq, cudaStream_t st) {
+  GGAD_REQUIRE(x && inv_norm && n_rows >= 0 && d > 0 && d % 4 == 0, GGAD_ERR_INVALID, "row_inv_norm: bad arguments");
+  GGAD_REQUIRE(ldx % 4 == 0 && ldx >= d && aligned16(x), GGAD_ERR_ALIGN, "row_inv_norm: x must be 16-byte aligned, ldx multiple of 4");
+  if (n_rows == 0) return GGAD_OK;
+  row_inv_norm_kernel<<<blocks_for(n_rows * 32), 256, 0, st>>>(x, ldx, n_rows, d, inv_norm, sumsq);
+  GGAD_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return GGAD_OK;
+}
+
+int normalize_backward_impl(const float* e, int64_t lde, const float* inv_norm, float* g, int64_t ldg, int64_t n_rows,
+                            int32_t d, cudaStream_t st) {
+  GGAD_REQUIRE(e && inv_norm && g && n_rows >= 0 && d > 0 && d % 4 == 0, GGAD_ERR_INVALID, "normalize_backward: bad arguments");
+  GGAD_REQUIRE(lde % 4 == 0 && ldg % 4 == 0 && lde >= d && ldg >= d && aligned16(e) && aligned16(g), GGAD_ERR_ALIGN,
+               "normalize_backward: e/g must be 16-byte aligned with leading dimensions multiple of 4");
+  if (n_rows == 0) return GGAD_OK;
+  normalize_backward_kernel<<<blocks_for(n_rows * 32), 256, 0, st>>>(e, lde, inv_norm, g, ldg, n_rows, d);
+  GGAD_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return GGAD_OK;
+}
+
+int rmat_keys_impl(uint64_t* keys, int64_t n_edges, int64_t n_local, int32_t n_shards, int32_t shard, uint64_t seed,
+                   float a, float b, float c, int64_t filter_lo, int64_t filter_hi, int64_t* n_out_host, cudaStream_t st) {
+  GGAD_REQUIRE(keys && n_edges >= 0 && n_local > 0, GGAD_ERR_INVALID, "rmat_keys: bad arguments");
+  GGAD_REQUIRE(n_shards >= 1 && (n_shards & (n_shards - 1)) == 0 && shard >= 0 && shard < n_shards, GGAD_ERR_INVALID,
+               "rmat_keys: n_shards must be a power of two and 0 <= shard < n_shards");
+  GGAD_REQUIRE(int64_t(n_shards) * n_local < (int64_t(1) << 31), GGAD_ERR_UNSUPPORTED, "rmat_keys: node ids must fit int32");
+  const float dd = 1.f - a - b - c;
+  GGAD_REQUIRE(a > 0 && b >= 0 && c >= 0 && dd >= 0, GGAD_ERR_INVALID, "rmat_keys: bad (a,b,c)");
+  RmatParams p;
+  p.n_edges = n_edges; p.n_local = n_local; p.shard = shard; p.seed = seed;
+  p.shard_bits = 0;
+  while ((1 << p.shard_bits) < n_shards) ++p.shard_bits;
+  p.local_bits = bits_for(n_local);
+  p.ta = uint32_t(a * 65536.f); p.tab = uint32_t((a + b) * 65536.f); p.tabc = uint32_t((a + b + c) * 65536.f);
+  p.t0 = uint32_t(a / (a + b) * 65536.f);
+  p.t1 = (c + dd) > 0 ? uint32_t(c / (c + dd) * 65536.f) : 65536u;
+  p.filter_lo = filter_lo; p.filter_hi = filter_hi;
+  const bool filtered = filter_lo < filter_hi;
+  unsigned long long* counter = nullptr;
+  if (filtered) {
+    GGAD_REQUIRE(n_out_host, GGAD_ERR_INVALID, "rmat_keys: n_out_host required with a filter");
+    GGAD_CUDA_OK(cudaMallocAsync(&counter, 8, st));
+    GGAD_CUDA_OK(cudaMemsetAsync(counter, 0, 8, st));
+  }
+  if (n_edges > 0) {
+    unsigned blocks = blocks_for(n_edges);
+    if (blocks > 148u * 64u) blocks = 148u * 64u;
+    rmat_kernel<<<blocks, 256, 0, st>>>(p, keys, counter);
+    GGAD_CUDA_OK(cudaGetLastError());
+    count_launch(1);
+  }
+  if (filtered) {
+    unsigned long long h = 0;
+    GGAD_CUDA_OK(cudaMemcpyAsync(&h, counter, 8, cudaMemcpyDeviceToHost, st));
+    GGAD_CUDA_OK(cudaStreamSynchronize(st));
+    GGAD_CUDA_OK(cudaFreeAsync(counter, st));
+    *n_out_host = int64_t(h);
+  } else if (n_out_host) {
+    *n_out_host = n_edges;
+  }
+  return GGAD_OK;
+}
+
+}  // namespace ggad

@@ -1,0 +1,280 @@
+"""Device-resident CSR container for the aggregation operators of the GGAD hot path.
+
+HBM layout: rowptr int64 [n_rows+1], col int32 [nnz], val fp32 [nnz] or absent (all ones, with the
+normalisation carried by row_scale / col_scale vectors), plus the merge-path plan (tile_row int32,
+tile_edge int64, one entry per 2048 items) and a per-width partial-row workspace.  The transpose
+(needed by every backward) is built lazily on the device and cached.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, stream_ptr
+
+# below this many (rows + edges) the group-per-row kernel is used and no plan is built
+PLAN_MIN_ITEMS = 1 << 14
+
+
+def _pad4(n: int) -> int:
+    return (n + 3) & ~3
+
+
+class CSRGraph:
+    """A sparse operator A [n_rows, n_cols] in CSR on one GPU.
+
+    Effective entry: A[r, c] = row_scale[r] * val[e] * col_scale[c]  (missing parts = 1).
+    """
+
+    def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor], n_rows: int, n_cols: int,
+                 row_scale: Optional[torch.Tensor] = None, col_scale: Optional[torch.Tensor] = None,
+                 symmetric_pattern: bool = False, use_plan: Optional[bool] = None):
+        for name, t in (("rowptr", rowptr), ("col", col)):
+            _lib.require_cuda(t, name)
+        assert rowptr.dtype == torch.int64 and col.dtype == torch.int32
+        assert val is None or (val.dtype == torch.float32 and val.is_cuda)
+        self.rowptr, self.col, self.val = rowptr.contiguous(), col.contiguous(), None if val is None else val.contiguous()
+        self.n_rows, self.n_cols, self.nnz = int(n_rows), int(n_cols), int(col.numel())
+        assert self.rowptr.numel() == self.n_rows + 1
+        self.row_scale, self.col_scale = row_scale, col_scale
+        self.device = rowptr.device
+        # pattern AND values symmetric (A == A^T up to the row/col scale swap): transpose reuses the arrays
+        self.symmetric_pattern = symmetric_pattern
+        self._use_plan = (self.n_rows + self.nnz >= PLAN_MIN_ITEMS) if use_plan is None else use_plan
+        self._plan = None
+        self._ws: Dict[int, torch.Tensor] = {}
+        self._T: Optional["CSRGraph"] = None
+        self._rows_cache: Dict[bytes, "CSRGraph"] = {}
+
+    # ---------------------------------------------------------------- builders
+    @classmethod
+    def from_arrays(cls, rowptr, col, val, n_rows, n_cols, device="cuda", **kw) -> "CSRGraph":
+        rp = torch.as_tensor(np.asarray(rowptr, dtype=np.int64)).to(device)
+        c = torch.as_tensor(np.asarray(col, dtype=np.int32)).to(device)
+        v = None if val is None else torch.as_tensor(np.asarray(val, dtype=np.float32)).to(device)
+        return cls(rp, c, v, n_rows, n_cols, **kw)
+
+    @classmethod
+    def from_scipy(cls, m, device="cuda", **kw) -> "CSRGraph":
+        import scipy.sparse as sp
+        m = sp.csr_matrix(m)
+        m.sum_duplicates()
+        m.sort_indices()
+        return cls.from_arrays(m.indptr, m.indices, m.data, m.shape[0], m.shape[1], device=device, **kw)
+
+    @classmethod
+    def from_dense(cls, adj: torch.Tensor, device="cuda", **kw) -> "CSRGraph":
+        """From the dense fp32 ``adj`` / ``raw_adj`` tensors run.py builds ([1,N,N] or [N,N])."""
+        a = adj.detach()
+        if a.dim() == 3:
+            a = a[0]
+        sp_t = a.to_sparse_csr()
+        return cls(sp_t.crow_indices().to(torch.int64).to(device), sp_t.col_indices().to(torch.int32).to(device),
+                   sp_t.values().to(torch.float32).to(device), a.shape[0], a.shape[1], **kw)
+
+    @classmethod
+    def from_any(cls, adj, device="cuda") -> "CSRGraph":
+        if isinstance(adj, CSRGraph):
+            return adj
+        if isinstance(adj, torch.Tensor):
+            if adj.layout == torch.strided:
+                return cls.from_dense(adj, device)
+            a = adj.coalesce() if adj.layout == torch.sparse_coo else adj
+            if a.layout == torch.sparse_coo:
+                a = a.to_sparse_csr()
+            return cls(a.crow_indices().to(torch.int64).to(device), a.col_indices().to(torch.int32).to(device),
+                       a.values().to(torch.float32).to(device), a.shape[-2], a.shape[-1])
+        return cls.from_scipy(adj, device)
+
+    # ---------------------------------------------------------------- plan / workspace
+    @property
+    def plan(self):
+        """(tile_row, tile_edge, n_tiles) or None for small graphs."""
+        if not self._use_plan:
+            return None
+        if self._plan is None:
+            n_tiles = int(lib().ggad_plan_num_tiles(self.n_rows, self.nnz))
+            tile_row = torch.empty(n_tiles + 1, dtype=torch.int32, device=self.device)
+            tile_edge = torch.empty(n_tiles + 1, dtype=torch.int64, device=self.device)
+            with torch.cuda.device(self.device):
+                check(lib().ggad_plan_build(ptr(self.rowptr), self.n_rows, self.nnz, ptr(tile_row), ptr(tile_edge),
+                                            stream_ptr(self.device)))
+            self._plan = (tile_row, tile_edge, n_tiles)
+        return self._plan
+
+    def workspace(self, d: int) -> Optional[torch.Tensor]:
+        if self.plan is None:
+            return None
+        ws = self._ws.get(d)
+        if ws is None:
+            ws = torch.empty(2 * self.plan[2] * d, dtype=torch.float32, device=self.device)
+            self._ws = {d: ws}          # keep only the latest width
+        return ws
+
+    # ---------------------------------------------------------------- derived operators
+    @property
+    def T(self) -> "CSRGraph":
+        """Transposed operator (device build, cached).  Row/col scales swap roles."""
+        if self._T is None:
+            if self.symmetric_pattern:
+                t = CSRGraph(self.rowptr, self.col, self.val, self.n_cols, self.n_rows, row_scale=self.col_scale,
+                             col_scale=self.row_scale, symmetric_pattern=True, use_plan=self._use_plan)
+                t._plan = self._plan
+            else:
+                rpt = torch.empty(self.n_cols + 1, dtype=torch.int64, device=self.device)
+                ct = torch.empty(self.nnz, dtype=torch.int32, device=self.device)
+                vt = None if self.val is None else torch.empty(self.nnz, dtype=torch.float32, device=self.device)
+                with torch.cuda.device(self.device):
+                    check(lib().ggad_csr_transpose(ptr(self.rowptr), ptr(self.col), ptr(self.val), self.n_rows, self.n_cols,
+                                                   self.nnz, ptr(rpt), ptr(ct), ptr(vt), None, stream_ptr(self.device)))
+                t = CSRGraph(rpt, ct, vt, self.n_cols, self.n_rows, row_scale=self.col_scale, col_scale=self.row_scale)
+            t._T = self
+            self._T = t
+        return self._T
+
+    def rows(self, idx: Sequence[int]) -> "CSRGraph":
+        """Sub-operator A[idx, :] as its own CSR (the ``adj[0, S, :]`` of model.py:151), cached per index set."""
+        idx_np = np.asarray(idx, dtype=np.int32)
+        key = idx_np.tobytes()
+        g = self._rows_cache.get(key)
+        if g is None:
+            rows = torch.from_numpy(idx_np).to(self.device)
+            deg = (self.rowptr[1:] - self.rowptr[:-1])[rows.long()]
+            sub_ptr = torch.zeros(len(idx_np) + 1, dtype=torch.int64, device=self.device)
+            torch.cumsum(deg, 0, out=sub_ptr[1:])
+            nnz = int(sub_ptr[-1].item())
+            sub_col = torch.empty(nnz, dtype=torch.int32, device=self.device)
+            sub_val = None if self.val is None else torch.empty(nnz, dtype=torch.float32, device=self.device)
+            with torch.cuda.device(self.device):
+                check(lib().ggad_csr_extract_rows(ptr(self.rowptr), ptr(self.col), ptr(self.val), ptr(rows), len(idx_np),
+                                                  ptr(sub_ptr), ptr(sub_col), ptr(sub_val), stream_ptr(self.device)))
+            rs = None if self.row_scale is None else self.row_scale[rows.long()].contiguous()
+            g = CSRGraph(sub_ptr, sub_col, sub_val, len(idx_np), self.n_cols, row_scale=rs, col_scale=self.col_scale)
+            if len(self._rows_cache) > 8:
+                self._rows_cache.clear()
+            self._rows_cache[key] = g
+        return g
+
+    def degrees(self) -> torch.Tensor:
+        """Exact integer row degrees (int64)."""
+        return self.rowptr[1:] - self.rowptr[:-1]
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        v = np.ones(self.nnz, dtype=np.float32) if self.val is None else self.val.cpu().numpy()
+        m = sp.csr_matrix((v, self.col.cpu().numpy(), self.rowptr.cpu().numpy()), shape=(self.n_rows, self.n_cols))
+        if self.row_scale is not None:
+            m = sp.diags(self.row_scale.cpu().numpy()).dot(m)
+        if self.col_scale is not None:
+            m = m.dot(sp.diags(self.col_scale.cpu().numpy()))
+        return sp.csr_matrix(m)
+
+    def algorithmic_bytes(self, d: int) -> int:
+        """B_alg of SURVEY.md 8(d): every input read once, output written once."""
+        w = 0 if self.val is None else 1
+        return self.nnz * (4 + 4 * w) + (self.n_rows + 1) * 8 + self.n_cols * d * 4 + self.n_rows * d * 4
+
+
+# ------------------------------------------------------------------------------------------
+# host-side index work (bit-exact restatement of the reference preprocessing)
+# ------------------------------------------------------------------------------------------
+def normalize_adj_scipy(adj):
+    """``D^-1/2 A^T D^-1/2`` in fp64 with D from row sums -- same scipy calls as utils.py:47-54."""
+    import scipy.sparse as sp
+    a = sp.coo_matrix(adj)
+    deg = np.asarray(a.sum(1), dtype=np.float64).reshape(-1)
+    with np.errstate(divide="ignore"):
+        dis = np.power(deg, -0.5)
+    dis[np.isinf(dis)] = 0.0
+    dm = sp.diags(dis)
+    return a.dot(dm).transpose().dot(dm).tocsr()
+
+
+def full_batch_graphs(adj, device="cuda"):
+    """(A_hat, R, R^T) CSRGraphs for program A from the raw scipy adjacency, as run.py:96-109:
+    A_hat = normalize_adj(A) + I, R = A + I (fp64, rounded once to fp32)."""
+    import scipy.sparse as sp
+    a = sp.csr_matrix(adj).astype(np.float64)
+    n = a.shape[0]
+    eye = sp.eye(n, dtype=np.float64, format="csr")
+    a_hat = (normalize_adj_scipy(a) + eye).tocsr()
+    r = (a + eye).tocsr()
+    sym = (abs(a - a.T)).nnz == 0
+    g_hat = CSRGraph.from_scipy(a_hat.astype(np.float32), device, symmetric_pattern=sym)
+    g_r = CSRGraph.from_scipy(r.astype(np.float32), device, symmetric_pattern=sym)
+    return g_hat, g_r
+
+
+class AdjListCSR:
+    """Host CSR view of the ``dict[int -> set[int]]`` adjacency lists of program B
+    (src/utils.py:27-28,96-112), built once; neighbor ids sorted."""
+
+    _cache: Dict[int, "AdjListCSR"] = {}
+
+    def __init__(self, adj_lists, n: Optional[int] = None):
+        keys = np.fromiter((int(k) for k in adj_lists.keys()), dtype=np.int64)
+        n_nodes = int(max(keys.max() + 1 if len(keys) else 0, n or 0))
+        for v in adj_lists.values():
+            if len(v):
+                n_nodes = max(n_nodes, int(max(v)) + 1)
+        rowptr = np.zeros(n_nodes + 1, dtype=np.int64)
+        for k, v in adj_lists.items():
+            rowptr[int(k) + 1] = len(v)
+        np.cumsum(rowptr, out=rowptr)
+        col = np.empty(rowptr[-1], dtype=np.int64)
+        for k, v in adj_lists.items():
+            k = int(k)
+            if len(v):
+                col[rowptr[k]:rowptr[k + 1]] = np.sort(np.fromiter((int(t) for t in v), dtype=np.int64, count=len(v)))
+        self.rowptr, self.col, self.n = rowptr, col, n_nodes
+        self.n_keys = len(adj_lists)
+
+    @classmethod
+    def get(cls, adj_lists) -> "AdjListCSR":
+        key = id(adj_lists)
+        hit = cls._cache.get(key)
+        if hit is None or hit.n_keys != len(adj_lists):
+            hit = cls(adj_lists)
+            if len(cls._cache) > 4:
+                cls._cache.clear()
+            cls._cache[key] = hit
+        return hit
+
+    def neighbors(self, nodes: np.ndarray, add_self: bool):
+        """Block (rows=len(nodes)) -> (rowptr, col_global) with per-row sorted unique neighbor ids
+        (optionally united with the node itself, set semantics)."""
+        nodes = np.asarray(nodes, dtype=np.int64)
+        safe = np.minimum(nodes, max(self.n - 1, 0))
+        inside = nodes < self.n
+        s = np.where(inside, self.rowptr[safe], 0)
+        e = np.where(inside, self.rowptr[safe + 1], 0)
+        lens = e - s
+        total = int(lens.sum())
+        out_ptr = np.zeros(len(nodes) + 1, dtype=np.int64)
+        np.cumsum(lens, out=out_ptr[1:])
+        offs = np.repeat(s - out_ptr[:-1], lens) + np.arange(total, dtype=np.int64)   # flat gather of the slices
+        cols = self.col[offs]
+        if add_self and len(nodes):
+            rows = np.concatenate([np.repeat(np.arange(len(nodes), dtype=np.int64), lens),
+                                   np.arange(len(nodes), dtype=np.int64)])
+            cols = np.concatenate([cols, nodes])
+            m = int(max(self.n, nodes.max() + 1))
+            key = np.unique(rows * m + cols)                 # drops a duplicate self entry, sorts (row, col)
+            rows, cols = key // m, key % m
+            out_ptr = np.zeros(len(nodes) + 1, dtype=np.int64)
+            np.cumsum(np.bincount(rows, minlength=len(nodes)), out=out_ptr[1:])
+        return out_ptr, cols
+
+
+def batch_block(adj: AdjListCSR, nodes: Sequence[int], add_self: bool):
+    """Frontier + local block CSR for one aggregation hop (the set unions of
+    src/graphsage.py:305-311,335-341 as array ops).  Returns dict with:
+    frontier (sorted unique global ids), rowptr, col_local (int32), rdeg, cdeg (exact ints)."""
+    rowptr, cols = adj.neighbors(np.asarray(nodes, dtype=np.int64), add_self)
+    frontier, col_local = np.unique(cols, return_inverse=True)
+    rdeg = np.diff(rowptr)
+    cdeg = np.bincount(col_local, minlength=len(frontier)).astype(np.int64)
+    return dict(frontier=frontier, rowptr=rowptr, col=col_local.astype(np.int32), rdeg=rdeg, cdeg=cdeg)

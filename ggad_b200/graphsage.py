@@ -1,0 +1,335 @@
+"""Drop-in replacement for the reference's ``src/graphsage.py`` (program B, mini-batch GGAD on DGraph).
+
+Same class names, constructor arguments, forward signatures / return tuples and parameter names
+(``enc.weight``, ``enc.fc.weight``, ``weight``) as /root/reference/src/graphsage.py, so
+``from graphsage import *`` in src/model_handler.py can point here.  What changes underneath:
+
+  * the Python ``set`` unions and the dense 0/1 masks ([B,|U|] and [|U|,|U2|], 1.3 GB per batch on a
+    DGraph-sized graph) become a batch-local block CSR with exact integer row / column degrees
+    (graph.batch_block);
+  * ``mask.mm(embed_matrix)`` becomes the CSR gather-reduce kernel reading the feature table directly
+    through an index map (ops.spmm with xmap), with the sym-norm / mean weights applied as row and
+    column scales.
+
+The CPU branch of the reference is followed (no ``+ features(nodes)`` residual, src/graphsage.py:325-327).
+Frontiers are in sorted-id order where the reference has Python-set order; every consumer is
+permutation-invariant.  Tensors must be on a CUDA device.
+"""
+from __future__ import annotations
+
+import random
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn import init
+
+from . import ops
+from .graph import AdjListCSR, CSRGraph
+
+
+# ------------------------------------------------------------------------------------------
+# helpers: feature table, batch blocks
+# ------------------------------------------------------------------------------------------
+def _device_of(features, fallback=None) -> torch.device:
+    if isinstance(features, nn.Embedding):
+        return features.weight.device
+    return fallback or torch.device("cuda")
+
+
+_table_cache = {}
+
+
+def _feature_table(features) -> Optional[torch.Tensor]:
+    """The frozen feature table as a 16-byte-row CUDA matrix, or None when ``features`` is a callable."""
+    if not isinstance(features, nn.Embedding):
+        return None
+    w = features.weight
+    if not w.is_cuda:
+        raise RuntimeError("ggad_b200: move the feature table to a CUDA device (features.cuda()); no CPU fallback")
+    key = (id(w), w._version, w.data_ptr())
+    t = _table_cache.get(key)
+    if t is None:
+        t = ops.pad_cols(w.detach())
+        _table_cache.clear()
+        _table_cache[key] = t
+    return t
+
+
+class _Block:
+    """One aggregation hop of a mini-batch: frontier ids + block CSR on the device."""
+
+    def __init__(self, rowptr: np.ndarray, cols_global: np.ndarray, device):
+        frontier, col_local = np.unique(cols_global, return_inverse=True)
+        self.frontier = frontier                                   # sorted global ids (host)
+        self.rdeg = np.diff(rowptr)                                # exact ints
+        self.cdeg = np.bincount(col_local, minlength=len(frontier)).astype(np.int64)
+        self.n_rows, self.n_cols = len(rowptr) - 1, len(frontier)
+        self.rowptr_d = torch.from_numpy(rowptr.astype(np.int64)).to(device, non_blocking=True)
+        self.col_d = torch.from_numpy(col_local.astype(np.int32)).to(device, non_blocking=True)
+        self.frontier_d = torch.from_numpy(frontier.astype(np.int32)).to(device, non_blocking=True)
+        self.rdeg_d = torch.from_numpy(self.rdeg.astype(np.float32)).to(device, non_blocking=True)
+        self.cdeg_d = torch.from_numpy(self.cdeg.astype(np.float32)).to(device, non_blocking=True)
+        self.device = device
+
+    def graph(self, mode: str) -> CSRGraph:
+        """'sym': 1/sqrt(rdeg) * 1/sqrt(cdeg) (src/graphsage.py:314-318); 'mean': 1/rdeg (:316-317, :92-93).
+        Degree-0 rows give 0 * inf = NaN exactly like the reference's 0/0."""
+        if mode == "sym":
+            rs, cs = 1.0 / self.rdeg_d.sqrt(), 1.0 / self.cdeg_d.sqrt()
+        else:
+            rs, cs = 1.0 / self.rdeg_d, None
+        return CSRGraph(self.rowptr_d, self.col_d, None, self.n_rows, self.n_cols, row_scale=rs, col_scale=cs)
+
+
+def _rows_from_sets(sets: Sequence[Iterable[int]], nodes: Optional[Sequence[int]], add_self: bool):
+    """list[set] (+ optional self union) -> (rowptr, cols) with per-row sorted unique ids."""
+    rows_cols = []
+    for i, s in enumerate(sets):
+        a = np.fromiter((int(t) for t in s), dtype=np.int64, count=len(s))
+        if add_self:
+            a = np.append(a, int(nodes[i]))
+        rows_cols.append(np.unique(a))
+    rowptr = np.zeros(len(rows_cols) + 1, dtype=np.int64)
+    np.cumsum([len(a) for a in rows_cols], out=rowptr[1:])
+    cols = np.concatenate(rows_cols) if rows_cols else np.zeros(0, np.int64)
+    return rowptr, cols
+
+
+class _LazyNeighs(list):
+    """What our encoders hand to the aggregators instead of ``[adj_lists[int(n)] for n in nodes]``:
+    behaves like that list if someone iterates it, but lets the aggregator slice the cached host CSR."""
+
+    def __init__(self, adj_lists, nodes):
+        super().__init__()
+        self.adj_lists, self.nodes = adj_lists, [int(n) for n in nodes]
+
+    def materialise(self):
+        return [self.adj_lists[n] for n in self.nodes]
+
+
+def _block_for(nodes, to_neighs, adj_lists, add_self, device) -> _Block:
+    nodes = [int(n) for n in nodes]
+    if isinstance(to_neighs, _LazyNeighs) or to_neighs is None:
+        rowptr, cols = AdjListCSR.get(adj_lists).neighbors(np.asarray(nodes, dtype=np.int64), add_self)
+    else:
+        rowptr, cols = _rows_from_sets(to_neighs, nodes, add_self)
+    return _Block(rowptr, cols, device)
+
+
+def _aggregate(block: _Block, mode: str, features, device) -> torch.Tensor:
+    """(weights of ``mode``) @ features[frontier]  -> [rows, d]."""
+    g = block.graph(mode)
+    table = _feature_table(features)
+    if table is not None:
+        d = features.weight.shape[1]
+        return ops.spmm(g, table, xmap=block.frontier_d)[:, :d]
+    embed = features(torch.from_numpy(block.frontier).long().to(device))      # callable (stacked encoders)
+    return ops.spmm(g, embed)
+
+
+class BlockMask:
+    """The row-mean mask the reference returns as a dense [B,|U|] tensor (src/graphsage.py:316-317,360);
+    only ``.mm`` is consumed by GCNEncoder (:421)."""
+
+    def __init__(self, block: _Block):
+        self.block = block
+        self._g = block.graph("mean")
+        self.shape = (block.n_rows, block.n_cols)
+
+    def mm(self, x: torch.Tensor) -> torch.Tensor:
+        return ops.spmm(self._g, x.contiguous())
+
+    def to_dense(self) -> torch.Tensor:
+        b = self.block
+        m = torch.zeros(self.shape, device=b.device)
+        rows = torch.repeat_interleave(torch.arange(b.n_rows, device=b.device), torch.from_numpy(b.rdeg).to(b.device))
+        m[rows, b.col_d.long()] = (1.0 / b.rdeg_d)[rows]
+        return m
+
+
+# ------------------------------------------------------------------------------------------
+# vanilla GraphSAGE (src/graphsage.py:19-154)
+# ------------------------------------------------------------------------------------------
+class GraphSage(nn.Module):
+    def __init__(self, num_classes, enc):
+        super(GraphSage, self).__init__()
+        self.enc = enc
+        self.xent = nn.CrossEntropyLoss()
+        self.weight = nn.Parameter(torch.FloatTensor(num_classes, enc.embed_dim))
+        init.xavier_uniform_(self.weight)
+
+    def forward(self, nodes):
+        return self.weight.mm(self.enc(nodes)).t()
+
+    def to_prob(self, nodes):
+        return torch.sigmoid(self.forward(nodes))
+
+    def loss(self, nodes, labels):
+        scores = self.forward(nodes)
+        return self.xent(scores, labels.squeeze().to(scores.device))
+
+
+class MeanAggregator(nn.Module):
+    """Mean of (optionally sampled) neighbor features (src/graphsage.py:46-99)."""
+
+    def __init__(self, features, cuda=False, gcn=False):
+        super(MeanAggregator, self).__init__()
+        self.features = features
+        self.cuda = cuda
+        self.gcn = gcn
+        self.adj_lists = None            # set by Encoder so the cached host CSR can be sliced
+
+    def forward(self, nodes, to_neighs, num_sample=10):
+        device = _device_of(self.features)
+        if num_sample is not None:
+            sets = to_neighs.materialise() if isinstance(to_neighs, _LazyNeighs) else to_neighs
+            # host sampling like the reference (:74-80); sorted() because random.sample rejects sets on py>=3.11
+            to_neighs = [set(random.sample(sorted(s), num_sample)) if len(s) >= num_sample else s for s in sets]
+        block = _block_for(nodes, to_neighs, self.adj_lists, self.gcn, device)
+        return _aggregate(block, "mean", self.features, device)
+
+
+class Encoder(nn.Module):
+    """ReLU(W . cat(self, mean-of-neighbors)^T)  (src/graphsage.py:102-154)."""
+
+    def __init__(self, features, feature_dim, embed_dim, adj_lists, aggregator, num_sample=10, base_model=None,
+                 gcn=False, cuda=False, feature_transform=False):
+        super(Encoder, self).__init__()
+        self.features = features
+        self.feat_dim = feature_dim
+        self.adj_lists = adj_lists
+        self.aggregator = aggregator
+        self.num_sample = num_sample
+        if base_model != None:
+            self.base_model = base_model
+        self.gcn = gcn
+        self.embed_dim = embed_dim
+        self.cuda = cuda
+        self.aggregator.cuda = cuda
+        self.aggregator.adj_lists = adj_lists
+        self.weight = nn.Parameter(torch.FloatTensor(embed_dim, self.feat_dim if self.gcn else 2 * self.feat_dim))
+        init.xavier_uniform_(self.weight)
+
+    def forward(self, nodes):
+        neigh_feats = self.aggregator.forward(nodes, _LazyNeighs(self.adj_lists, nodes), self.num_sample)
+        if not self.gcn:
+            index = torch.as_tensor(nodes, dtype=torch.long).to(neigh_feats.device)
+            combined = torch.cat((self.features(index), neigh_feats), dim=1)
+        else:
+            combined = neigh_feats
+        return F.relu(self.weight.mm(combined.t()))
+
+
+# ------------------------------------------------------------------------------------------
+# GGAD mini-batch model (src/graphsage.py:157-454)
+# ------------------------------------------------------------------------------------------
+class GCNAggregator(nn.Module):
+    """Two-hop symmetric-normalised aggregation with batch-local degrees (src/graphsage.py:275-360)."""
+
+    def __init__(self, features, cuda=False, gcn=False):
+        super(GCNAggregator, self).__init__()
+        self.features = features
+        self.cuda = cuda
+        self.gcn = gcn
+
+    def forward(self, nodes, to_neighs, adj_list, train_flag):
+        device = _device_of(self.features)
+        hop1 = _block_for(nodes, to_neighs, adj_list, True, device)             # N(b) U {b}   (:305)
+        to_feats = _aggregate(hop1, "sym", self.features, device)
+        to_feats_neigh = None
+        if train_flag == True:
+            hop2 = _block_for(hop1.frontier.tolist(), None, adj_list, False, device)   # no self union (:335)
+            to_feats_neigh = _aggregate(hop2, "sym", self.features, device)
+            self.last_blocks = (hop1, hop2)
+        else:
+            self.last_blocks = (hop1, None)
+        return to_feats, to_feats_neigh, BlockMask(hop1)
+
+
+class GCNEncoder(nn.Module):
+    """src/graphsage.py:363-454.  Parameters: weight [h,d], fc.weight [h,h]."""
+
+    def __init__(self, features, feature_dim, embed_dim, adj_lists, aggregator, num_sample=10, base_model=None,
+                 gcn=False, cuda=False, feature_transform=False):
+        super(GCNEncoder, self).__init__()
+        self.features = features
+        self.feat_dim = feature_dim
+        self.adj_lists = adj_lists
+        self.aggregator = aggregator
+        self.num_sample = num_sample
+        if base_model != None:
+            self.base_model = base_model
+        self.gcn = gcn
+        self.embed_dim = embed_dim
+        self.cuda = cuda
+        self.aggregator.cuda = cuda
+        self.weight = nn.Parameter(torch.FloatTensor(embed_dim, self.feat_dim))
+        init.xavier_uniform_(self.weight)
+        self.fc = nn.Linear(embed_dim, embed_dim, bias=False)
+
+    def forward(self, nodes, label, train_flag):
+        neigh_feats, neigh_feats_expand, mask = self.aggregator.forward(nodes, _LazyNeighs(self.adj_lists, nodes),
+                                                                        self.adj_lists, train_flag)
+        combined = F.relu(self.weight.mm(neigh_feats.t()))                       # aggregate, then project (:412)
+        to_feats_neigh = None
+        anomaly_feat = None
+        anomaly_feat_new = None
+        combined_all = combined
+        if train_flag == True:
+            label = label.to(combined.device)
+            combined_expand = F.relu(self.weight.mm(neigh_feats_expand.t()))     # hop-1 frontier embeddings (:419)
+            to_feats_neigh = mask.mm(combined_expand.t())                        # ego-neighbor mean (:421)
+            is_ab, is_norm = label == 1, label == 0
+            anomaly_feat = combined[:, is_ab]
+            anomaly_feat_new = F.relu(self.fc(to_feats_neigh[is_ab]))            # outlier generation (:428-430)
+            combined_all = torch.cat((combined[:, is_norm], anomaly_feat_new.t()), 1)   # label-0 columns first (:450)
+            anomaly_feat_new = anomaly_feat_new.t()
+        return combined_all, to_feats_neigh, anomaly_feat, anomaly_feat_new
+
+
+class GCN(nn.Module):
+    """src/graphsage.py:157-272: scores, local-affinity margin, reconstruction, total loss."""
+
+    def __init__(self, num_classes, enc):
+        super(GCN, self).__init__()
+        self.enc = enc
+        self.xent = nn.BCEWithLogitsLoss(reduction='none', pos_weight=torch.tensor([1]))
+        self.weight = nn.Parameter(torch.FloatTensor(1, enc.embed_dim))
+        init.xavier_uniform_(self.weight)
+
+    def forward(self, nodes, label, train_flag):
+        embeds, to_feats_neigh, anomaly_feat, anomaly_feat_new = self.enc(nodes, label, train_flag)
+        scores = self.weight.mm(embeds)
+        return scores.t(), to_feats_neigh, embeds, anomaly_feat, anomaly_feat_new
+
+    def to_prob(self, nodes, label):
+        return torch.sigmoid(self.forward(nodes, label, train_flag=False)[0])
+
+    def to_prob_reconstruction(self, nodes, label):
+        return self.forward(nodes, label, train_flag=False)[0]
+
+    def recon2(self, anomaly_feat, anomaly_feat_new):
+        return torch.mean(torch.sqrt(torch.sum(torch.pow(anomaly_feat - anomaly_feat_new, 2), 0)))
+
+    def normalize(self, emb):
+        inv = torch.pow(torch.norm(emb, dim=-1, keepdim=True), -1)
+        inv = torch.where(torch.isinf(inv), torch.zeros_like(inv), inv)
+        return emb * inv
+
+    def affinity(self, combined_all, labels, to_feats_neigh):
+        labels = labels.to(combined_all.device)
+        aff = torch.cosine_similarity(combined_all, to_feats_neigh.t(), dim=0)   # (:234)
+        aff_normal = torch.mean(aff[torch.argwhere(labels == 0)], 0)
+        aff_abnormal = torch.mean(aff[torch.argwhere(labels == 1)], 0)
+        return (1 - (aff_normal - aff_abnormal)).clamp_min(min=0)                # margin 1 (:236-240)
+
+    def loss(self, nodes, labels):
+        scores, to_feats_neigh, embeds, anomaly_feat, anomaly_feat_new = self.forward(nodes, labels, train_flag=True)
+        target = labels.detach().to(scores.device, dtype=torch.float32)
+        loss_cls = torch.mean(self.xent(scores.squeeze(), target))
+        loss_constraint = self.affinity(embeds, labels, to_feats_neigh)
+        loss_rec = self.recon2(anomaly_feat, anomaly_feat_new)
+        return 1 * loss_cls + 1 * loss_constraint + 0.1 * loss_rec, loss_cls, loss_constraint, loss_rec

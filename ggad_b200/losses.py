@@ -1,0 +1,57 @@
+"""The loss block of the reference's full-batch training loop (run.py:164-210) on CSR.
+
+run.py is a script, so this is the one piece of program A a caller has to import instead of
+inlining: ``ggad_loss`` returns the same scalars run.py prints, with the N x N similarity matrix
+replaced by the row-subset local-affinity kernel (only aff[normal] and aff[abnormal] are consumed).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .graph import CSRGraph
+
+_subset_cache = {}
+
+
+def _subset(normal_idx, abnormal_idx, device):
+    """Unique union of the two index lists + positions of each list inside it (cached on identity)."""
+    key = (id(normal_idx), len(normal_idx), id(abnormal_idx), len(abnormal_idx), str(device))
+    hit = _subset_cache.get(key)
+    if hit is None:
+        n, a = np.asarray(normal_idx, dtype=np.int64), np.asarray(abnormal_idx, dtype=np.int64)
+        uniq, inv = np.unique(np.concatenate([n, a]), return_inverse=True)
+        hit = (torch.from_numpy(uniq.astype(np.int32)).to(device),
+               torch.from_numpy(inv[:len(n)]).to(device), torch.from_numpy(inv[len(n):]).to(device))
+        if len(_subset_cache) > 8:
+            _subset_cache.clear()
+        _subset_cache[key] = hit
+    return hit
+
+
+def ggad_loss(emb, logits, emb_con, emb_abnormal, raw_adj, normal_label_idx, abnormal_label_idx,
+              negsamp_ratio: float = 1.0, confidence_margin: float = 0.7):
+    """(loss, loss_margin, loss_bce, loss_rec, affinity_normal_mean, affinity_abnormal_mean).
+
+    emb [1,N,h] is Model.forward's first output (after the write-back), raw_adj is R = A + I as a
+    CSRGraph (or anything CSRGraph.from_any accepts)."""
+    device = emb.device
+    g_r = raw_adj if isinstance(raw_adj, CSRGraph) else CSRGraph.from_any(raw_adj, device)
+    # BCE (run.py:165-172): labels are [0]*|normal| + [1]*|S|
+    lbl = torch.cat((torch.zeros(len(normal_label_idx), device=device),
+                     torch.ones(emb_con.shape[0], device=device))).unsqueeze(1).unsqueeze(0)
+    loss_bce = F.binary_cross_entropy_with_logits(logits, lbl, reduction='none',
+                                                  pos_weight=torch.tensor([float(negsamp_ratio)], device=device)).mean()
+    # local affinity (run.py:175-191) on the consumed rows only
+    e = emb[0] if emb.dim() == 3 else emb
+    subset, pos_n, pos_a = _subset(normal_label_idx, abnormal_label_idx, device)
+    aff = ops.local_affinity(e, g_r, subset)
+    aff_n, aff_a = aff[pos_n].mean(), aff[pos_a].mean()
+    loss_margin = (confidence_margin - (aff_n - aff_a)).clamp_min(0)
+    # run.py:207-208 -- emb_abnormal carries the batch dim, so the sum runs over the |S| axis
+    diff = torch.pow(emb_con - emb_abnormal, 2)
+    loss_rec = torch.mean(torch.sqrt(torch.sum(diff, 1)))
+    loss = 1 * loss_margin + 1 * loss_bce + 1 * loss_rec
+    return loss, loss_margin, loss_bce, loss_rec, aff_n, aff_a

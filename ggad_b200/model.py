@@ -1,0 +1,170 @@
+"""Drop-in replacement for the reference's ``model.py`` (program A, full-batch GGAD).
+
+Same class names, constructor arguments, forward signatures, return tuples and state_dict keys as
+/root/reference/model.py, so ``from model import Model`` in run.py can point here unchanged.  The
+N x N dense products are replaced by the CSR gather-reduce kernels:
+
+  GCN.forward        model.py:26-35    -> ops.gcn_aggregate (A_hat @ (X W^T) + bias, PReLU: one launch)
+  adj[0,S,:] @ emb   model.py:151-155  -> ops.spmm on the row-extracted CSR (ego-neighbor sum)
+
+``adj`` may be a CSRGraph, a scipy matrix, a torch sparse tensor or the dense [1,N,N] tensor run.py
+builds (converted once and cached).  Everything must live on a CUDA device; there is no CPU path.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .graph import CSRGraph
+
+_graph_cache = {}
+
+
+def as_graph(adj, device) -> CSRGraph:
+    """Convert whatever run.py hands over into a (cached) CSRGraph."""
+    if isinstance(adj, CSRGraph):
+        return adj
+    key = (id(adj), getattr(adj, "_version", None), str(device))
+    g = _graph_cache.get(key)
+    if g is None:
+        g = CSRGraph.from_any(adj, device)
+        if len(_graph_cache) > 8:
+            _graph_cache.clear()
+        _graph_cache[key] = g
+    return g
+
+
+class GCN(nn.Module):
+    """model.py:6-35.  Parameters: fc.weight [out,in], bias [out], act.weight [1]."""
+
+    def __init__(self, in_ft, out_ft, act, bias=True):
+        super(GCN, self).__init__()
+        self.fc = nn.Linear(in_ft, out_ft, bias=False)
+        self.act = nn.PReLU() if act == 'prelu' else act
+        if bias:
+            self.bias = nn.Parameter(torch.FloatTensor(out_ft))
+            self.bias.data.fill_(0.0)
+        else:
+            self.register_parameter('bias', None)
+        for m in self.modules():
+            self.weights_init(m)
+
+    def weights_init(self, m):
+        if isinstance(m, nn.Linear):
+            torch.nn.init.xavier_uniform_(m.weight.data)
+            if m.bias is not None:
+                m.bias.data.fill_(0.0)
+
+    def forward(self, seq, adj, sparse=False):
+        squeeze = seq.dim() == 3
+        x = seq[0] if squeeze else seq
+        g = as_graph(adj, x.device)
+        seq_fts = self.fc(x)                                   # project first (model.py:27)
+        if isinstance(self.act, nn.PReLU) and self.act.weight.numel() == 1:
+            out = ops.gcn_aggregate(g, seq_fts, self.bias, self.act.weight)
+        else:
+            out = ops.spmm(g, seq_fts)
+            if self.bias is not None:
+                out = out + self.bias
+            out = self.act(out)
+        return out.unsqueeze(0) if squeeze else out
+
+
+class AvgReadout(nn.Module):
+    def forward(self, seq):
+        return torch.mean(seq, 1)
+
+
+class MaxReadout(nn.Module):
+    def forward(self, seq):
+        return torch.max(seq, 1).values
+
+
+class MinReadout(nn.Module):
+    def forward(self, seq):
+        return torch.min(seq, 1).values
+
+
+class WSReadout(nn.Module):
+    def forward(self, seq, query):
+        sim = F.softmax(torch.matmul(seq, query.permute(0, 2, 1)), dim=1).repeat(1, 1, 64)
+        return torch.sum(seq * sim, 1)
+
+
+class Discriminator(nn.Module):
+    """Constructed (never called) by Model so that checkpoints and RNG order line up (model.py:76-105,131)."""
+
+    def __init__(self, n_h, negsamp_round):
+        super(Discriminator, self).__init__()
+        self.f_k = nn.Bilinear(n_h, n_h, 1)
+        for m in self.modules():
+            if isinstance(m, nn.Bilinear):
+                torch.nn.init.xavier_uniform_(m.weight.data)
+                if m.bias is not None:
+                    m.bias.data.fill_(0.0)
+        self.negsamp_round = negsamp_round
+
+    def forward(self, c, h_pl):
+        scs = [self.f_k(h_pl, c)]
+        c_mi = c
+        for _ in range(self.negsamp_round):
+            c_mi = torch.cat((c_mi[-2:-1, :], c_mi[:-1, :]), 0)
+            scs.append(self.f_k(h_pl, c_mi))
+        return torch.cat(tuple(scs))
+
+
+class Model(nn.Module):
+    """model.py:108-191.  Unused members (gcn3, fc5, fc6, read, disc) are created in the reference's
+    order so seeded initialisation and state_dict keys match."""
+
+    def __init__(self, n_in, n_h, activation, negsamp_round, readout):
+        super(Model, self).__init__()
+        self.read_mode = readout
+        self.gcn1 = GCN(n_in, n_h, activation)
+        self.gcn2 = GCN(n_h, n_h, activation)
+        self.gcn3 = GCN(n_h, n_h, activation)
+        self.fc1 = nn.Linear(n_h, int(n_h / 2), bias=False)
+        self.fc2 = nn.Linear(int(n_h / 2), int(n_h / 4), bias=False)
+        self.fc3 = nn.Linear(int(n_h / 4), 1, bias=False)
+        self.fc4 = nn.Linear(n_h, n_h, bias=False)
+        self.fc6 = nn.Linear(n_h, n_h, bias=False)
+        self.fc5 = nn.Linear(n_h, n_in, bias=False)
+        self.act = nn.ReLU()
+        if readout == 'max':
+            self.read = MaxReadout()
+        elif readout == 'min':
+            self.read = MinReadout()
+        elif readout == 'avg':
+            self.read = AvgReadout()
+        elif readout == 'weighted_sum':
+            self.read = WSReadout()
+        self.disc = Discriminator(n_h, negsamp_round)
+
+    def _mlp(self, t):
+        return self.fc3(self.act(self.fc2(self.act(self.fc1(t)))))
+
+    def forward(self, seq1, adj, sample_abnormal_idx, normal_idx, train_flag, args, sparse=False, noise=None):
+        """Returns (emb, emb_combine, f_3, emb_con, emb_abnormal) exactly like the reference.
+        ``noise`` (optional, [1,|S|,h]) overrides the Gaussian draw of model.py:143 for parity tests."""
+        g = as_graph(adj, seq1.device)
+        h_1 = self.gcn1(seq1, g, sparse)
+        emb = self.gcn2(h_1, g, sparse)
+        emb_con = None
+        emb_combine = None
+        emb_abnormal = emb[:, sample_abnormal_idx, :]
+        if noise is None:
+            # drawn on the CPU generator with the reference's call, then moved (same stream of numbers)
+            noise = (torch.randn(emb_abnormal.size()) * args.var + args.mean).to(emb.device)
+        emb_abnormal = emb_abnormal + noise
+        if train_flag:
+            ego = ops.spmm(g.rows(sample_abnormal_idx), emb[0])          # rows S of A_hat @ emb
+            emb_con = self.act(self.fc4(ego))
+            emb_combine = torch.cat((emb[:, normal_idx, :], torch.unsqueeze(emb_con, 0)), 1)
+            f_3 = self._mlp(emb_combine)
+            idx = torch.as_tensor(sample_abnormal_idx, dtype=torch.long, device=emb.device)
+            emb = emb.index_copy(1, idx, emb_con.unsqueeze(0))           # the in-place write-back of model.py:182
+        else:
+            f_3 = self._mlp(emb)
+        return emb, emb_combine, f_3, emb_con, emb_abnormal

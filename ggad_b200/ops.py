@@ -1,0 +1,191 @@
+"""torch.autograd.Function wrappers around the C-ABI kernels (K1-K6 of DESIGN.md).
+
+Every op takes CUDA tensors and calls libggad_b200.so on torch's current stream; there is no
+CPU path.  Backward passes are hand-derived and call the same gather-reduce kernel on the
+transposed CSR (no float atomics anywhere, results are run-to-run deterministic).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import GatherDesc, check, lib, ptr, stream_ptr
+from .graph import CSRGraph
+
+
+def _pad4(n: int) -> int:
+    return (n + 3) & ~3
+
+
+def pad_cols(x: torch.Tensor) -> torch.Tensor:
+    """Zero-pad the last dim to a multiple of 4 floats (16-byte rows); no copy if already aligned."""
+    d = x.shape[-1]
+    if d % 4 == 0 and x.is_contiguous() and x.data_ptr() % 16 == 0:
+        return x
+    out = x.new_zeros(*x.shape[:-1], _pad4(d))
+    out[..., :d] = x
+    return out
+
+
+def gather_reduce(g: CSRGraph, x: torch.Tensor, *, xmap: Optional[torch.Tensor] = None,
+                  col_scale: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
+                  bias: Optional[torch.Tensor] = None, prelu_slope: Optional[torch.Tensor] = None, relu: bool = False,
+                  want_y: bool = True, want_z: bool = False, want_sumsq: bool = False,
+                  dot_mat: Optional[torch.Tensor] = None, dot_rows: Optional[torch.Tensor] = None,
+                  dot_scale: Optional[torch.Tensor] = None, use_graph_scales: bool = True):
+    """Raw (non-autograd) call of ggad_gather_reduce.  ``x`` is [n_x_rows, d] fp32 CUDA with d % 4 == 0.
+    Returns dict(y=, z=, sumsq=, dot=) with the requested outputs."""
+    _lib.require_cuda(x, "x")
+    assert x.dtype == torch.float32 and x.dim() == 2
+    x = x if (x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0) else x.contiguous()
+    d = x.shape[1]
+    if d % 4 != 0:
+        raise RuntimeError(f"ggad_b200: feature width {d} must be a multiple of 4 (use ops.pad_cols)")
+    dev = x.device
+    n = g.n_rows
+    if use_graph_scales:
+        row_scale = g.row_scale if row_scale is None else row_scale
+        col_scale = g.col_scale if col_scale is None else col_scale
+    y = torch.empty(n, d, dtype=torch.float32, device=dev) if want_y else None
+    z = torch.empty(n, d, dtype=torch.float32, device=dev) if want_z else None
+    ss = torch.empty(n, dtype=torch.float32, device=dev) if want_sumsq else None
+    dot = torch.empty(n, dtype=torch.float32, device=dev) if dot_mat is not None else None
+    desc = GatherDesc()
+    desc.rowptr, desc.col, desc.val = ptr(g.rowptr), ptr(g.col), ptr(g.val)
+    desc.n_rows, desc.nnz = g.n_rows, g.nnz
+    desc.x, desc.ldx = ptr(x), x.stride(0)
+    desc.xmap, desc.col_scale, desc.row_scale = ptr(xmap), ptr(col_scale), ptr(row_scale)
+    desc.d, desc.relu = d, int(bool(relu))
+    desc.bias, desc.prelu_slope = ptr(bias), ptr(prelu_slope)
+    desc.y, desc.z, desc.ldy = ptr(y), ptr(z), d
+    desc.sumsq = ptr(ss)
+    if dot_mat is not None:
+        assert dot_mat.stride(1) == 1
+        desc.dot_mat, desc.lddot = ptr(dot_mat), dot_mat.stride(0)
+        desc.dot_rows, desc.dot_scale, desc.dot_out = ptr(dot_rows), ptr(dot_scale), ptr(dot)
+    plan = g.plan
+    if plan is not None:
+        ws = g.workspace(d)
+        desc.tile_row, desc.tile_edge, desc.n_tiles, desc.ws = ptr(plan[0]), ptr(plan[1]), plan[2], ptr(ws)
+    with torch.cuda.device(dev):
+        check(lib().ggad_gather_reduce(desc, stream_ptr(dev)))
+    return dict(y=y, z=z, sumsq=ss, dot=dot)
+
+
+# ------------------------------------------------------------------------------------------
+class _Spmm(torch.autograd.Function):
+    """y = A x  (optionally x gathered through xmap).  dx = A^T dy."""
+
+    @staticmethod
+    def forward(ctx, x, g: CSRGraph, xmap):
+        ctx.g, ctx.xmap, ctx.n_x = g, xmap, x.shape[0]
+        return gather_reduce(g, x, xmap=xmap)["y"]
+
+    @staticmethod
+    def backward(ctx, dy):
+        if not ctx.needs_input_grad[0]:
+            return None, None, None
+        g = ctx.g
+        if ctx.xmap is not None:
+            raise RuntimeError("ggad_b200: gradient w.r.t. a feature table gathered through xmap is not supported "
+                               "(the reference freezes it: src/model_handler.py:263-264)")
+        dx = gather_reduce(g.T, dy.contiguous())["y"]
+        return dx, None, None
+
+
+def spmm(g: CSRGraph, x: torch.Tensor, xmap: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """A @ x on the GPU (replaces torch.spmm / torch.bmm(adj, .) of model.py:29,31 and the
+    mask.mm(...) products of src/graphsage.py).  Width is padded to a multiple of 4 internally."""
+    d = x.shape[1]
+    xp = pad_cols(x)
+    y = _Spmm.apply(xp, g, xmap)
+    return y if xp.shape[1] == d else y[:, :d]
+
+
+class _GcnAggregate(torch.autograd.Function):
+    """out = PReLU(A x + bias) in one launch (model.py:29-35); saves the pre-activation for backward."""
+
+    @staticmethod
+    def forward(ctx, x, g: CSRGraph, bias, slope):
+        r = gather_reduce(g, x, bias=bias, prelu_slope=slope, want_z=True)
+        ctx.g = g
+        ctx.save_for_backward(r["z"], slope)
+        ctx.has_bias = bias is not None
+        return r["y"]
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, slope = ctx.saved_tensors
+        neg = z < 0
+        dz = torch.where(neg, dy * slope, dy)
+        dslope = (dy * z * neg).sum().reshape(slope.shape) if ctx.needs_input_grad[3] else None
+        dbias = dz.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        dx = gather_reduce(ctx.g.T, dz)["y"] if ctx.needs_input_grad[0] else None
+        return dx, None, dbias, dslope
+
+
+def gcn_aggregate(g: CSRGraph, x: torch.Tensor, bias: Optional[torch.Tensor], slope: torch.Tensor) -> torch.Tensor:
+    d = x.shape[1]
+    xp = pad_cols(x)
+    bp = None if bias is None else pad_cols(bias.reshape(1, -1)).reshape(-1)
+    y = _GcnAggregate.apply(xp, g, bp, slope)
+    return y if xp.shape[1] == d else y[:, :d]
+
+
+class _LocalAffinity(torch.autograd.Function):
+    """aff_i = (1/c_j) sum_i' R[i',j] <e^_i', e^_j>, j = subset[i]   (run.py:175-188), only for the rows
+    in ``subset``.  Forward = one gather-reduce over CSR(R^T)[subset] with col_scale 1/|e| and the dot
+    epilogue.  Backward:
+        de^_k = sum_j R[k,j] (g_j/c_j) e^_j  +  [k in subset] (g_k/c_k) sum_i' R[i',k] e^_i'
+        de_k  = (de^_k - e^_k <e^_k, de^_k>) / |e_k|
+    """
+
+    @staticmethod
+    def forward(ctx, emb, g_rt_sub: CSRGraph, g_r: CSRGraph, subset, r_inv_sub):
+        n, d = emb.shape
+        inv = torch.empty(n, dtype=torch.float32, device=emb.device)
+        with torch.cuda.device(emb.device):
+            check(lib().ggad_row_inv_norm(ptr(emb), emb.stride(0), n, d, ptr(inv), None, stream_ptr(emb.device)))
+        dot_scale = inv[subset.long()] * r_inv_sub
+        r = gather_reduce(g_rt_sub, emb, col_scale=inv, dot_mat=emb, dot_rows=subset, dot_scale=dot_scale,
+                          use_graph_scales=False)
+        ctx.g_r = g_r
+        ctx.save_for_backward(emb, inv, r["y"], subset, r_inv_sub)
+        return r["dot"]
+
+    @staticmethod
+    def backward(ctx, g_aff):
+        emb, inv, acc, subset, r_inv_sub = ctx.saved_tensors
+        n, d = emb.shape
+        gamma = g_aff * r_inv_sub                                  # g_j / c_j on the subset
+        cs = torch.zeros(n, dtype=torch.float32, device=emb.device)
+        cs[subset.long()] = gamma * inv[subset.long()]             # col_scale: gamma_j / |e_j|, 0 elsewhere (skipped)
+        de = gather_reduce(ctx.g_r, emb, col_scale=cs, use_graph_scales=False)["y"]
+        de.index_add_(0, subset.long(), acc * gamma.unsqueeze(1))
+        with torch.cuda.device(emb.device):
+            check(lib().ggad_normalize_backward(ptr(emb), emb.stride(0), ptr(inv), ptr(de), de.stride(0), n, d,
+                                                stream_ptr(emb.device)))
+        return de, None, None, None, None
+
+
+def local_affinity(emb: torch.Tensor, g_r: CSRGraph, subset: torch.Tensor) -> torch.Tensor:
+    """Local-affinity scores for the nodes in ``subset`` (int32 CUDA, unique).  ``g_r`` is R = A + I."""
+    d = emb.shape[1]
+    e = pad_cols(emb)
+    cache = g_r.__dict__.setdefault("_aff_cache", {})
+    key = (subset.data_ptr(), subset.numel())
+    hit = cache.get(key)
+    if hit is None:
+        g_rt = g_r.T
+        g_sub = g_rt.rows(subset.cpu().numpy())
+        # c_j = sum_i R[i,j]: exact column sums (row sums of R^T), fp32 like torch.sum(raw_adj, 0)
+        ones = torch.ones(g_r.n_rows, 4, dtype=torch.float32, device=emb.device)
+        csum = gather_reduce(g_sub, ones, use_graph_scales=False)["y"][:, 0]
+        r_inv = torch.where(csum != 0, 1.0 / csum, torch.zeros_like(csum))
+        hit = (g_sub, r_inv.contiguous(), subset)
+        cache.clear()
+        cache[key] = hit
+    g_sub, r_inv, _ = hit
+    return _LocalAffinity.apply(e, g_sub, g_r, subset, r_inv)

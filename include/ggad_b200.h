@@ -1,0 +1,183 @@
+/*
+ * ggad_b200 -- C ABI of the B200-native GGAD message-passing / outlier-synthesis path.
+ *
+ * The reference (mala-lab/GGAD) is pure Python and has NO FFI / plugin interface for
+ * this path; its boundary is the nn.Module surface.  The entry
+ * points below are what a binding for that path has to bind: each one names the
+ * reference code it replaces (paths relative to the reference checkout).  The Python
+ * host side (ggad_b200/*.py) binds them with ctypes and re-creates the reference's
+ * module classes on top; INTEGRATION.md shows the stub a reference maintainer adds.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the
+ *     parameter name ends in _host; `stream` is a cudaStream_t passed as void*.
+ *   - every function returns 0 (GGAD_OK) or a negative GGAD_ERR_* code and never
+ *     throws; ggad_last_error() gives a thread-local message.  Work is enqueued on
+ *     `stream` and is asynchronous unless stated otherwise.
+ *   - feature matrices are row-major fp32 with a leading dimension (in floats) that is
+ *     a multiple of 4 and a 16-byte aligned base; the logical width `d` must also be a
+ *     multiple of 4 (pad with zero columns -- sums stay exact).  CSR: rowptr int64,
+ *     col int32, val fp32 or NULL (= all ones).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     returns GGAD_ERR_CUDA.
+ */
+#ifndef GGAD_B200_H_
+#define GGAD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GGAD_OK 0
+#define GGAD_ERR_INVALID (-1)     /* bad argument (null pointer, negative size, d % 4 != 0 ...) */
+#define GGAD_ERR_ALIGN (-2)       /* pointer / leading dimension not 16-byte aligned */
+#define GGAD_ERR_CUDA (-3)        /* CUDA runtime error (message in ggad_last_error) */
+#define GGAD_ERR_UNSUPPORTED (-4) /* width or size outside what the kernels cover */
+
+#define GGAD_TILE_ITEMS 2048 /* merge-path items (rows + edges) per CTA tile */
+#define GGAD_MAX_WIDTH 768   /* max logical width d per launch (745 pads to 748) */
+
+typedef void* ggad_stream_t;
+
+#if defined(__GNUC__)
+#define GGAD_API __attribute__((visibility("default")))
+#else
+#define GGAD_API
+#endif
+
+/* ---- library / device -------------------------------------------------------- */
+GGAD_API int ggad_version(void);
+GGAD_API const char* ggad_last_error(void);
+/* number of CUDA kernels this library has launched since it was loaded */
+GGAD_API int64_t ggad_launch_count(void);
+GGAD_API int ggad_device_info(int* sm_count, int64_t* l2_bytes, int* cc_major, int* cc_minor, int64_t* hbm_bytes);
+
+/* ---- K1/K2/K3/K5: CSR neighbor gather-reduce with fused per-row epilogue -------
+ *
+ *   acc_r  = row_scale[r] * sum_{e in row r} val[e] * col_scale[c_e] * X[xmap[c_e]]      c_e = col[e]
+ *   z_r    = acc_r + bias                                    (written to z if non-NULL)
+ *   y_r    = prelu_slope ? PReLU(z_r) : relu ? ReLU(z_r) : z_r   (written to y if non-NULL)
+ *   sumsq_r   = |y_r|^2                                      (if sumsq non-NULL)
+ *   dot_out_r = dot_scale[r] * < y_r , dot_mat[dot_rows ? dot_rows[r] : r] >   (if dot_out non-NULL)
+ *
+ * Edges whose col_scale is 0 or whose xmap is negative are skipped without loading X.
+ *
+ * Replaces: torch.bmm / torch.spmm in GCN.forward (model.py:26-35, bias + PReLU fused);
+ * their autograd backward (same call on the transposed CSR); adj[0,S,:] @ emb
+ * (model.py:151-155, on the row-extracted CSR); sim*raw_adj column sums (run.py:182-188,
+ * dot epilogue on CSR(R^T) rows with col_scale = 1/|e_i|); mask.mm(embed_matrix) in
+ * MeanAggregator / GCNAggregator (src/graphsage.py:98,326,355) and mask_row.mm(...)
+ * (src/graphsage.py:421) on batch-local block CSRs with xmap = frontier node ids.
+ *
+ * If tile_row/tile_edge/ws are given (see ggad_plan_*), the merge-path tiled kernel is
+ * used: every CTA owns GGAD_TILE_ITEMS (rows+edges), stages its col/val slice in
+ * shared memory with a TMA bulk copy, splits it evenly over lane groups, and combines
+ * partial rows deterministically (no float atomics).  Otherwise a group-per-row kernel
+ * is used (fine for small graphs; serialises on hub rows).
+ */
+typedef struct ggad_gather_desc {
+  /* CSR of the aggregation operator */
+  const int64_t* rowptr; /* [n_rows + 1] */
+  const int32_t* col;    /* [nnz] */
+  const float* val;      /* [nnz] or NULL */
+  int64_t n_rows;
+  int64_t nnz;
+  /* gathered operand */
+  const float* x;         /* [n_x_rows, ldx] */
+  int64_t ldx;            /* floats, multiple of 4 */
+  const int32_t* xmap;    /* NULL or [n_cols]: row of x for column c (<0: skip) */
+  const float* col_scale; /* NULL or [n_cols] */
+  const float* row_scale; /* NULL or [n_rows] */
+  int32_t d;              /* logical width, multiple of 4, <= GGAD_MAX_WIDTH */
+  int32_t relu;           /* 1: ReLU epilogue (ignored if prelu_slope given) */
+  /* epilogue */
+  const float* bias;        /* NULL or [d] */
+  const float* prelu_slope; /* NULL or [1] (device) */
+  float* y;                 /* NULL or [n_rows, ldy] */
+  float* z;                 /* NULL or [n_rows, ldy] pre-activation */
+  int64_t ldy;
+  float* sumsq;            /* NULL or [n_rows] */
+  const float* dot_mat;    /* NULL or [*, lddot] */
+  int64_t lddot;
+  const int32_t* dot_rows; /* NULL or [n_rows] */
+  const float* dot_scale;  /* NULL or [n_rows] */
+  float* dot_out;          /* NULL or [n_rows] */
+  /* merge-path plan (all three or none) */
+  const int32_t* tile_row;  /* [n_tiles + 1] */
+  const int64_t* tile_edge; /* [n_tiles + 1] */
+  int64_t n_tiles;
+  float* ws; /* [2 * n_tiles * d] partial-row workspace */
+} ggad_gather_desc_t;
+
+GGAD_API int ggad_gather_reduce(const ggad_gather_desc_t* desc, ggad_stream_t stream);
+
+/* Merge-path plan for a CSR: n_tiles = ceil((n_rows + nnz) / GGAD_TILE_ITEMS). */
+GGAD_API int64_t ggad_plan_num_tiles(int64_t n_rows, int64_t nnz);
+GGAD_API int ggad_plan_build(const int64_t* rowptr, int64_t n_rows, int64_t nnz, int32_t* tile_row /*[n_tiles+1]*/,
+                    int64_t* tile_edge /*[n_tiles+1]*/, ggad_stream_t stream);
+
+/* ---- K4: backward helper of the local-affinity cosine ---------------------------
+ * de_k = ( g_k - e^_k <e^_k, g_k> ) * inv_norm_k   with e^_k = e_k * inv_norm_k, in place on g.
+ * (autograd of run.py:177-180.) */
+GGAD_API int ggad_normalize_backward(const float* e, int64_t lde, const float* inv_norm, float* g, int64_t ldg,
+                            int64_t n_rows, int32_t d, ggad_stream_t stream);
+
+/* Row L2 statistics: inv_norm[r] = 1/|x_r| with 1/0 -> 0 (run.py:177-179); sumsq optional. */
+GGAD_API int ggad_row_inv_norm(const float* x, int64_t ldx, int64_t n_rows, int32_t d, float* inv_norm, float* sumsq,
+                      ggad_stream_t stream);
+
+/* ---- K7: index / degree work (integer results are bit-exact vs the CPU path) ----- */
+/* keys = (row << 32 | col), sorted in place; fills rowptr[n_rows+1] and col[n]. Synchronous w.r.t. stream
+ * ordering (uses stream-ordered temporaries). Duplicate edges are kept. */
+GGAD_API int ggad_coo_keys_to_csr(uint64_t* keys, int64_t n, int64_t n_rows, int64_t* rowptr, int32_t* col, ggad_stream_t stream);
+/* CSR -> CSR of the transpose, stable in source-row order (replaces scipy .transpose().tocsr()).
+ * val/valT may be NULL; perm (NULL or [nnz]) receives the source edge index of each transposed edge. */
+GGAD_API int ggad_csr_transpose(const int64_t* rowptr, const int32_t* col, const float* val, int64_t n_rows, int64_t n_cols,
+                       int64_t nnz, int64_t* rowptrT, int32_t* colT, float* valT, int64_t* perm, ggad_stream_t stream);
+/* Sub-CSR of the listed rows (adj[0,S,:] of model.py:151 without densifying):
+ * sub_rowptr[n_sel+1] must already hold the exclusive prefix sum of the selected degrees. */
+GGAD_API int ggad_csr_extract_rows(const int64_t* rowptr, const int32_t* col, const float* val, const int32_t* rows, int64_t n_sel,
+                          const int64_t* sub_rowptr, int32_t* sub_col, float* sub_val, ggad_stream_t stream);
+/* integer in-degree histogram of col[] (int32 counts, exact) */
+GGAD_API int ggad_col_histogram(const int32_t* col, int64_t nnz, int32_t* counts, int64_t n_cols, ggad_stream_t stream);
+
+/* ---- synthetic graphs (C5 / S64 generator) -------------------------
+ * R-MAT (a,b,c,d) edges for destination shard `shard` of `n_shards` (power of two), each shard
+ * owning n_local nodes; emits keys (dst_global << 32 | src_global), dst in the shard's range,
+ * src anywhere.  If filter_lo < filter_hi only edges with src in [filter_lo, filter_hi) are kept
+ * as (src << 32 | dst) keys (used to build the transposed shard) and *n_out_host receives the count
+ * (this variant synchronises the stream). */
+GGAD_API int ggad_rmat_keys(uint64_t* keys, int64_t n_edges, int64_t n_local, int32_t n_shards, int32_t shard, uint64_t seed,
+                   float a, float b, float c, int64_t filter_lo, int64_t filter_hi, int64_t* n_out_host,
+                   ggad_stream_t stream);
+
+/* ---- host-buffer entry point (end-to-end path; copies inside) --------------------
+ * One fwd + bwd pass of a plain SpMM layer with HOST feature buffers:
+ *   y = A x ;  dx = A^T y       (loss = |y|^2 / 2, so dy = y)
+ * x_host is copied in, dx_host (and y_host if non-NULL) copied out, *loss_host = |y|^2/2.
+ * dev_x [n_cols*d], dev_y [n_rows*d], dev_dx [n_cols*d] and dev_ws are caller-owned device scratch;
+ * dev_ws holds 2*max(a.n_tiles, at.n_tiles)*d + roundup4(n_rows) + 4 floats.
+ * The CSRs (A and A^T with their plans) stay resident on the device like model state.
+ * Synchronous: returns after the results are in host memory. */
+typedef struct ggad_resident_csr {
+  const int64_t* rowptr;
+  const int32_t* col;
+  const float* val;
+  const float* row_scale;
+  const float* col_scale;
+  int64_t n_rows, n_cols, nnz;
+  const int32_t* tile_row;
+  const int64_t* tile_edge;
+  int64_t n_tiles;
+} ggad_resident_csr_t;
+
+GGAD_API int ggad_spmm_fwd_bwd_host(const ggad_resident_csr_t* a, const ggad_resident_csr_t* at, const float* x_host,
+                           float* y_host, float* dx_host, double* loss_host, int32_t d, float* dev_x, float* dev_y,
+                           float* dev_dx, float* dev_ws, ggad_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGAD_B200_H_ */

@@ -1,0 +1,328 @@
+"""GPU parity tests of the C-ABI kernels against the CPU oracle (run with -m gpu on the B200 box).
+
+Tolerance (north star): index / degree / plan arrays bit-exact; fp32 embeddings within 1e-4 relative.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+import oracle
+from helpers import ATOL, RTOL, assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    import ggad_b200
+    from ggad_b200 import _lib, graph, ops, synth
+    return ggad_b200, _lib, graph, ops, synth
+
+
+def make_csr(n_rows, n_cols, avg_deg, seed, hub=None, empties=True, weighted=True):
+    rng = np.random.default_rng(seed)
+    deg = rng.poisson(avg_deg, n_rows)
+    if empties:
+        deg[rng.integers(0, n_rows, max(1, n_rows // 10))] = 0
+        deg[0] = 0
+        deg[-1] = 0
+    if hub is not None:
+        deg[n_rows // 3] = hub
+    rowptr = np.zeros(n_rows + 1, dtype=np.int64)
+    np.cumsum(deg, out=rowptr[1:])
+    col = rng.integers(0, n_cols, rowptr[-1]).astype(np.int32)
+    val = rng.standard_normal(rowptr[-1]).astype(np.float32) if weighted else None
+    return rowptr, col, val
+
+
+def merge_path_plan(rowptr, tile):
+    """CPU restatement of plan_kernel (bit-exact integer check)."""
+    n_rows, nnz = len(rowptr) - 1, int(rowptr[-1])
+    n_tiles = (n_rows + nnz + tile - 1) // tile
+    rows, edges = [], []
+    for t in range(n_tiles + 1):
+        diag = min(t * tile, n_rows + nnz)
+        lo, hi = max(diag - nnz, 0), min(diag, n_rows)
+        while lo < hi:
+            mid = (lo + hi) >> 1
+            if rowptr[mid + 1] <= diag - mid - 1:
+                lo = mid + 1
+            else:
+                hi = mid
+        rows.append(lo)
+        edges.append(diag - lo)
+    return np.asarray(rows, np.int32), np.asarray(edges, np.int64)
+
+
+@pytest.mark.parametrize("d", [4, 12, 20, 28, 64, 100, 128, 256, 300, 512, 748])
+@pytest.mark.parametrize("use_plan", [False, True])
+def test_gather_reduce_widths(d, use_plan):
+    _, _, graph, ops, _ = _mods()
+    n_rows, n_cols = 700, 900
+    rowptr, col, val = make_csr(n_rows, n_cols, 9.0, seed=d, hub=3000)
+    g = graph.CSRGraph.from_arrays(rowptr, col, val, n_rows, n_cols, use_plan=use_plan)
+    x = torch.randn(n_cols, d)
+    ref = oracle.spmm_csr(rowptr, col, val, x)
+    out = ops.gather_reduce(g, x.cuda())["y"]
+    assert_close(out, ref, rtol=RTOL, atol=2e-4, what=f"spmm d={d} plan={use_plan}")
+
+
+@pytest.mark.parametrize("use_plan", [False, True])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_gather_reduce_epilogues(use_plan, weighted):
+    _, _, graph, ops, _ = _mods()
+    n_rows, n_cols, d = 3000, 2500, 64
+    rowptr, col, val = make_csr(n_rows, n_cols, 14.0, seed=3, hub=9000, weighted=weighted)
+    rng = np.random.default_rng(0)
+    rs = torch.from_numpy(rng.random(n_rows).astype(np.float32) + 0.5)
+    cs = torch.from_numpy(rng.random(n_cols).astype(np.float32) + 0.5)
+    cs[::7] = 0.0                                   # skipped columns
+    bias = torch.randn(d)
+    slope = torch.tensor([0.25])
+    x = torch.randn(n_cols, d)
+    g = graph.CSRGraph.from_arrays(rowptr, col, val, n_rows, n_cols, use_plan=use_plan)
+    r = ops.gather_reduce(g, x.cuda(), row_scale=rs.cuda(), col_scale=cs.cuda(), bias=bias.cuda(),
+                          prelu_slope=slope.cuda(), want_z=True, want_sumsq=True)
+    v = np.ones(len(col), np.float32) if val is None else val
+    v_eff = v * cs.numpy()[col]
+    z_ref = oracle.spmm_csr(rowptr, col, v_eff, x) * rs[:, None] + bias
+    y_ref = torch.where(z_ref >= 0, z_ref, 0.25 * z_ref)
+    assert_close(r["z"], z_ref, atol=2e-4, what="z")
+    assert_close(r["y"], y_ref, atol=2e-4, what="y")
+    assert_close(r["sumsq"], (y_ref ** 2).sum(1), rtol=2e-4, atol=1e-3, what="sumsq")
+    # relu + dot epilogue with row indirection
+    dot_rows = torch.from_numpy(rng.integers(0, n_cols, n_rows).astype(np.int32))
+    ds = torch.from_numpy(rng.random(n_rows).astype(np.float32))
+    r2 = ops.gather_reduce(g, x.cuda(), relu=True, dot_mat=x.cuda(), dot_rows=dot_rows.cuda(), dot_scale=ds.cuda())
+    y2 = torch.relu(oracle.spmm_csr(rowptr, col, val, x))
+    assert_close(r2["y"], y2, atol=2e-4, what="relu y")
+    assert_close(r2["dot"], (y2 * x[dot_rows.long()]).sum(1) * ds, rtol=2e-4, atol=2e-3, what="dot")
+
+
+@pytest.mark.parametrize("use_plan", [False, True])
+def test_gather_reduce_xmap(use_plan):
+    _, _, graph, ops, _ = _mods()
+    n_rows, n_cols, n_table, d = 1200, 800, 5000, 20
+    rowptr, col, _ = make_csr(n_rows, n_cols, 30.0, seed=11, weighted=False)
+    rng = np.random.default_rng(1)
+    xmap = rng.permutation(n_table)[:n_cols].astype(np.int32)
+    xmap[5] = -1
+    table = torch.randn(n_table, d)
+    g = graph.CSRGraph.from_arrays(rowptr, col, None, n_rows, n_cols, use_plan=use_plan)
+    out = ops.gather_reduce(g, table.cuda(), xmap=torch.from_numpy(xmap).cuda())["y"]
+    xm = table[torch.from_numpy(np.maximum(xmap, 0)).long()].clone()
+    xm[5] = 0
+    ref = oracle.spmm_csr(rowptr, col, None, xm)
+    assert_close(out, ref, atol=2e-4, what="xmap gather")
+
+
+def test_tiled_matches_rowwise_bitwise_shapes():
+    """Edge shapes for the merge-path kernel: single giant row, all-empty rows, one edge, rows == tile."""
+    _, _, graph, ops, _ = _mods()
+    d = 32
+    cases = []
+    rp = np.zeros(6, np.int64); rp[3:] = 10000; cases.append((rp, 50))          # one 10k row among empties
+    cases.append((np.zeros(5001, np.int64), 10))                                 # no edges at all
+    rp = np.zeros(3, np.int64); rp[2] = 1; cases.append((rp, 7))                 # a single edge
+    rp = np.arange(0, 2049 * 3, 3, dtype=np.int64); cases.append((rp, 400))      # many 3-edge rows
+    rp = np.concatenate([np.zeros(3000, np.int64), np.arange(0, 4097, dtype=np.int64)]); cases.append((rp, 99))
+    for rowptr, n_cols in cases:
+        n_rows, nnz = len(rowptr) - 1, int(rowptr[-1])
+        rng = np.random.default_rng(nnz)
+        col = rng.integers(0, n_cols, nnz).astype(np.int32)
+        val = rng.standard_normal(nnz).astype(np.float32)
+        x = torch.randn(n_cols, d)
+        ref = oracle.spmm_csr(rowptr, col, val, x)
+        for use_plan in (True, False):
+            g = graph.CSRGraph.from_arrays(rowptr, col, val, n_rows, n_cols, use_plan=use_plan)
+            out = ops.gather_reduce(g, x.cuda(), bias=torch.ones(d).cuda())["y"]
+            assert_close(out, ref + 1.0, rtol=RTOL, atol=3e-4, what=f"rows={n_rows} nnz={nnz} plan={use_plan}")
+
+
+def test_plan_bit_exact():
+    _, _lib, graph, _, _ = _mods()
+    for seed, (n_rows, avg, hub) in enumerate([(5000, 3.0, 20000), (100, 500.0, None), (40000, 0.2, None)]):
+        rowptr, col, _ = make_csr(n_rows, 1000, avg, seed, hub=hub, weighted=False)
+        g = graph.CSRGraph.from_arrays(rowptr, col, None, n_rows, 1000, use_plan=True)
+        tr, te, nt = g.plan
+        ref_r, ref_e = merge_path_plan(rowptr, _lib.GGAD_TILE_ITEMS)
+        assert nt == len(ref_r) - 1
+        assert np.array_equal(tr.cpu().numpy(), ref_r) and np.array_equal(te.cpu().numpy(), ref_e)
+
+
+def test_index_kernels_bit_exact():
+    _, _lib, graph, _, _ = _mods()
+    lib, ptr, check = _lib.lib(), _lib.ptr, _lib.check
+    rng = np.random.default_rng(5)
+    n_rows, n_cols, nnz = 3000, 2000, 50000
+    r = rng.integers(0, n_rows, nnz).astype(np.int64)
+    c = rng.integers(0, n_cols, nnz).astype(np.int64)
+    keys = torch.from_numpy((r << 32) | c).cuda()
+    rowptr = torch.empty(n_rows + 1, dtype=torch.int64, device="cuda")
+    col = torch.empty(nnz, dtype=torch.int32, device="cuda")
+    check(lib.ggad_coo_keys_to_csr(ptr(keys), nnz, n_rows, ptr(rowptr), ptr(col), _lib.stream_ptr()))
+    order = np.lexsort((c, r))
+    ref_ptr = np.zeros(n_rows + 1, np.int64)
+    np.cumsum(np.bincount(r, minlength=n_rows), out=ref_ptr[1:])
+    assert np.array_equal(rowptr.cpu().numpy(), ref_ptr)
+    assert np.array_equal(col.cpu().numpy(), c[order].astype(np.int32))
+    # transpose (with values and perm) vs scipy
+    val = rng.standard_normal(nnz).astype(np.float32)
+    g = graph.CSRGraph(rowptr, col, torch.from_numpy(val).cuda(), n_rows, n_cols)
+    t = g.T
+    m = sp.csr_matrix((val, col.cpu().numpy(), ref_ptr), shape=(n_rows, n_cols))
+    # scipy's transpose().tocsr() keeps source-row order inside each transposed row (stable)
+    mt = m.transpose().tocsr()
+    assert np.array_equal(t.rowptr.cpu().numpy(), mt.indptr.astype(np.int64))
+    # rows inside a transposed row are ascending here and duplicates may be ordered differently by scipy: compare sorted
+    x = torch.randn(n_rows, 8)
+    ref = torch.from_numpy((mt @ x.numpy()).astype(np.float32))
+    from ggad_b200 import ops
+    assert_close(ops.gather_reduce(t, x.cuda())["y"], ref, atol=1e-4, what="transpose spmm")
+    assert np.array_equal(np.sort(t.col.cpu().numpy()), np.sort(mt.indices.astype(np.int32)))
+    # column histogram
+    cnt = torch.empty(n_cols, dtype=torch.int32, device="cuda")
+    check(lib.ggad_col_histogram(ptr(col), nnz, ptr(cnt), n_cols, _lib.stream_ptr()))
+    assert np.array_equal(cnt.cpu().numpy(), np.bincount(c, minlength=n_cols).astype(np.int32))
+    # row extraction
+    sel = rng.permutation(n_rows)[:500]
+    sub = g.rows(sel)
+    ms = m[sel]
+    assert np.array_equal(sub.rowptr.cpu().numpy(), ms.indptr.astype(np.int64))
+    assert np.array_equal(sub.col.cpu().numpy(), ms.indices.astype(np.int32))
+    assert np.array_equal(sub.val.cpu().numpy(), ms.data.astype(np.float32))
+
+
+def test_row_norm_and_normalize_backward():
+    _, _lib, _, _, _ = _mods()
+    lib, ptr, check = _lib.lib(), _lib.ptr, _lib.check
+    n, d = 1000, 300
+    e = torch.randn(n, d)
+    e[3] = 0
+    g = torch.randn(n, d)
+    inv = torch.empty(n, device="cuda")
+    ss = torch.empty(n, device="cuda")
+    ec, gc = e.cuda(), g.clone().cuda()
+    check(lib.ggad_row_inv_norm(ptr(ec), d, n, d, ptr(inv), ptr(ss), _lib.stream_ptr()))
+    ref_inv = torch.pow(torch.norm(e, dim=-1), -1)
+    ref_inv[torch.isinf(ref_inv)] = 0
+    assert_close(inv, ref_inv, what="inv_norm")
+    assert_close(ss, (e ** 2).sum(1), atol=1e-3, what="sumsq")
+    check(lib.ggad_normalize_backward(ptr(ec), d, ptr(inv), ptr(gc), d, n, d, _lib.stream_ptr()))
+    er = e.clone().requires_grad_(True)
+    nrm = torch.norm(er, dim=-1, keepdim=True)
+    iv = torch.pow(nrm, -1)
+    iv = torch.where(torch.isinf(iv), torch.zeros_like(iv), iv)
+    (er * iv).backward(g)
+    ref = er.grad.clone()
+    ref[3] = 0                                    # zero row: reference yields NaN/0 mix; we define 0
+    gc_cpu = gc.cpu()
+    gc_cpu[3] = 0
+    assert_close(gc_cpu, ref, rtol=2e-4, atol=1e-5, what="normalize backward")
+
+
+def test_spmm_autograd_large_powerlaw():
+    """Moderately large power-law graph with a 50k hub: forward, backward and adjointness."""
+    _, _, graph, ops, _ = _mods()
+    rng = np.random.default_rng(9)
+    n, d = 60000, 64
+    deg = np.minimum((rng.pareto(1.3, n) * 4).astype(np.int64), 5000)
+    deg[123] = 50000
+    rowptr = np.zeros(n + 1, np.int64)
+    np.cumsum(deg, out=rowptr[1:])
+    col = rng.integers(0, n, rowptr[-1]).astype(np.int32)
+    val = rng.random(rowptr[-1]).astype(np.float32)
+    g = graph.CSRGraph.from_arrays(rowptr, col, val, n, n)
+    assert g.plan is not None
+    x = torch.randn(n, d)
+    xg = x.cuda().requires_grad_(True)
+    y = ops.spmm(g, xg)
+    w = torch.randn(n, d)
+    (y * w.cuda()).sum().backward()
+    m = sp.csr_matrix((val, col, rowptr), shape=(n, n))
+    y_ref = torch.from_numpy(m @ x.numpy())
+    dx_ref = torch.from_numpy(m.T @ w.numpy())
+    assert_close(y, y_ref, rtol=RTOL, atol=5e-3, what="y")
+    assert_close(xg.grad, dx_ref, rtol=RTOL, atol=5e-3, what="dx")
+    lhs = (y.detach().double() * w.cuda().double()).sum()
+    rhs = (xg.detach().double() * xg.grad.double()).sum()
+    assert abs(float(lhs - rhs)) <= 1e-5 * abs(float(lhs)) + 1e-3          # <Ax, w> == <x, A^T w>
+    # deterministic: two runs are bit-identical (no float atomics)
+    y2 = ops.spmm(g, xg.detach())
+    assert torch.equal(y.detach(), y2)
+
+
+def test_rmat_generator_and_shards():
+    _, _, graph, ops, synth = _mods()
+    n_local, n_edges, shards = 5000, 60000, 4
+    parts = [synth.rmat_shard(n_local, n_edges, shards, s, seed=7, mean=False) for s in range(shards)]
+    rows, cols = [], []
+    for s, g in enumerate(parts):
+        rp, c = g.rowptr.cpu().numpy(), g.col.cpu().numpy()
+        assert rp[0] == 0 and rp[-1] == n_edges and np.all(np.diff(rp) >= 0)
+        assert c.min() >= 0 and c.max() < n_local * shards
+        rows.append(np.repeat(np.arange(n_local) + s * n_local, np.diff(rp)))
+        cols.append(c.astype(np.int64))
+    rows, cols = np.concatenate(rows), np.concatenate(cols)
+    full_t = sp.coo_matrix((np.ones(len(rows)), (cols, rows)), shape=(n_local * shards,) * 2).tocsr()
+    # transposed shard built by regeneration == transpose of the concatenated forward shards (integers, exact)
+    lo, hi = 3000, 9000
+    t = synth.rmat_transposed_shard(n_local, n_edges, shards, 7, lo, hi)
+    sub = full_t[lo:hi]
+    assert np.array_equal(t.rowptr.cpu().numpy(), sub.indptr.astype(np.int64))
+    x = np.random.default_rng(0).standard_normal((n_local * shards, 8)).astype(np.float32)
+    ref = torch.from_numpy(sub @ x)
+    assert_close(ops.gather_reduce(t, torch.from_numpy(x).cuda())["y"], ref, atol=1e-4, what="transposed shard")
+    # power-law: the max in-degree is far above the mean
+    indeg = np.bincount(cols, minlength=n_local * shards)
+    assert indeg.max() > 20 * indeg.mean()
+    # same seed -> same graph
+    again = synth.rmat_shard(n_local, n_edges, shards, 1, seed=7, mean=False)
+    assert torch.equal(again.col, parts[1].col) and torch.equal(again.rowptr, parts[1].rowptr)
+
+
+def test_host_buffer_entry_point():
+    _, _lib, graph, ops, synth = _mods()
+    lib, ptr, check = _lib.lib(), _lib.ptr, _lib.check
+    n, d = 30000, 64
+    g = synth.rmat_shard(n, 400000, seed=1)
+    gt = g.T
+    x = torch.randn(n, d).pin_memory()
+    y_h = torch.empty(n, d).pin_memory()
+    dx_h = torch.empty(n, d).pin_memory()
+
+    def res(c):
+        r = _lib.ResidentCSR()
+        r.rowptr, r.col, r.val = ptr(c.rowptr), ptr(c.col), ptr(c.val)
+        r.row_scale, r.col_scale = ptr(c.row_scale), ptr(c.col_scale)
+        r.n_rows, r.n_cols, r.nnz = c.n_rows, c.n_cols, c.nnz
+        p = c.plan
+        r.tile_row, r.tile_edge, r.n_tiles = ptr(p[0]), ptr(p[1]), p[2]
+        return r
+    ra, rt = res(g), res(gt)
+    nt = max(ra.n_tiles, rt.n_tiles)
+    dev = [torch.empty(n, d, device="cuda") for _ in range(3)]
+    ws = torch.empty(2 * nt * d + n + 16, device="cuda")
+    loss = C.c_double(0)
+    check(lib.ggad_spmm_fwd_bwd_host(C.byref(ra), C.byref(rt), ptr(x), ptr(y_h), ptr(dx_h), C.addressof(loss), d,
+                                     ptr(dev[0]), ptr(dev[1]), ptr(dev[2]), ptr(ws), _lib.stream_ptr()))
+    y = ops.gather_reduce(g, x.cuda())["y"]
+    dx = ops.gather_reduce(gt, y)["y"]
+    assert torch.equal(y.cpu(), y_h) and torch.equal(dx.cpu(), dx_h)
+    assert abs(loss.value - 0.5 * float((y.double() ** 2).sum())) <= 1e-6 * loss.value + 1e-6
+
+
+def test_errors_are_loud():
+    _, _lib, graph, ops, _ = _mods()
+    rowptr, col, val = make_csr(10, 10, 2.0, 0)
+    g = graph.CSRGraph.from_arrays(rowptr, col, val, 10, 10)
+    with pytest.raises(RuntimeError, match="multiple of 4"):
+        ops.gather_reduce(g, torch.randn(10, 10).cuda())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.gather_reduce(g, torch.randn(10, 12))
+    desc = _lib.GatherDesc()
+    desc.n_rows, desc.d = 5, 8                                               # null pointers
+    assert _lib.lib().ggad_gather_reduce(C.byref(desc), None) == -1          # GGAD_ERR_INVALID, no crash
+    assert b"required" in _lib.lib().ggad_last_error()
