@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""Headline benchmark: edges/s of one CSR SpMM layer pass (forward + backward) on R-MAT power-law graphs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload S64|C4|custom] [--impl native|reference]
+
+Workload (config.workload): ``S64`` = one C5 shard per GPU -- 6.25 M nodes / 125 M edges / d = 64 per GPU
+(at N = 8 this is BASELINE.json's 50 M-node / 1 B-edge graph) -- weak scaling.  A step is
+    Y  = A[lo:hi, :] X          (mean aggregation over the rank's destination range)   + all-gather(Y)
+    dX = A^T[lo':hi', :] dY     (dY = Y, loss = |Y|^2/2; transposed CSR, no atomics)   + all-gather(dX)
+`value` = total edges of all ranks / step time with everything resident in HBM (inputs >> L2, so no flush
+is needed); `e2e` = same pass with the features coming from pinned host memory and dX + loss read back,
+through the C-ABI host entry point (ggad_spmm_fwd_bwd_host) at N = 1.  `roofline` is for the forward
+gather kernel: algorithmic bytes (SURVEY.md 8d B_alg) / CUDA-event time / measured HBM peak.
+`--impl reference` times the reference's own CPU path for this op (torch.spmm on a CSR adjacency,
+model.py:28-29, + autograd backward) on a bounded sample of the same generator.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nodes per GPU, edges per GPU, width)
+    "S64": (6_250_000, 125_000_000, 64),
+    "C4": (3_700_550, 73_105_508, 20),          # DGraph-shaped full-graph pass, d=17 padded to 20
+    "C3": (39_357, 21_222_543, 300),            # T-Finance-shaped layer-2 pass (L2-resident table)
+    "C2": (11_944, 4_398_392, 300),             # Amazon-shaped layer-2 pass
+    "tiny": (50_000, 1_000_000, 64),
+}
+RMAT = (0.57, 0.19, 0.19)
+
+
+# ----------------------------------------------------------------------------------------------
+# host-side R-MAT (numpy) for the CPU legs -- same distribution as the device generator
+# ----------------------------------------------------------------------------------------------
+def rmat_csr_numpy(n: int, m: int, seed: int):
+    rng = np.random.default_rng(seed)
+    bits = max(1, int(np.ceil(np.log2(n))))
+    a, b, c = RMAT
+    dst = np.zeros(m, dtype=np.int64)
+    src = np.zeros(m, dtype=np.int64)
+    todo = np.arange(m)
+    for _ in range(32):
+        k = len(todo)
+        d_ = np.zeros(k, dtype=np.int64)
+        s_ = np.zeros(k, dtype=np.int64)
+        for _l in range(bits):
+            u = rng.random(k)
+            q = (u >= a).astype(np.int64) + (u >= a + b) + (u >= a + b + c)
+            d_ = (d_ << 1) | (q >> 1)
+            s_ = (s_ << 1) | (q & 1)
+        dst[todo], src[todo] = d_, s_
+        bad = (d_ >= n) | (s_ >= n)
+        todo = todo[bad]
+        if len(todo) == 0:
+            break
+    dst %= n
+    src %= n
+    order = np.lexsort((src, dst))
+    dst, src = dst[order], src[order]
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(dst, minlength=n), out=rowptr[1:])
+    return rowptr, src.astype(np.int32)
+
+
+def cpu_reference_leg(n: int, m: int, d: int, steps: int, warmup: int):
+    """The reference's CPU implementation of the op (torch.spmm CSR fwd + autograd bwd) on all host threads."""
+    import oracle
+    rowptr, col = rmat_csr_numpy(n, m, seed=0)
+    deg = np.diff(rowptr).astype(np.float32)
+    val = np.repeat(np.where(deg > 0, 1.0 / np.maximum(deg, 1), 0).astype(np.float32), np.diff(rowptr))
+    x = torch.randn(n, d)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        oracle.torch_spmm_cpu_baseline(rowptr, col, val, x, backward=True)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    t = float(np.mean(times))
+    return dict(value=m / t, unit="edges/s", cores=torch.get_num_threads(), kind="port",
+                sample=f"R-MAT N={n} nnz={m} d={d} (same generator as the GPU workload), torch.spmm CSR fwd+bwd, "
+                       f"{steps} steps of {t:.2f} s on {torch.get_num_threads()} threads / {os.cpu_count()} cpus"), t
+
+
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampler running during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.th.join(2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+def native(args):
+    import torch.distributed as dist
+    from ggad_b200 import _lib, dist as gdist, ops, synth
+    from ggad_b200.graph import CSRGraph
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_local, m_local, d = args.nodes, args.edges, args.width
+    n_glob = n_local * world
+    lib = _lib.lib()
+
+    # ---- graph shards (generated on device) ----
+    t_build = time.perf_counter()
+    fwd = synth.rmat_shard(n_local, m_local, world, rank, seed=args.seed, device=dev, mean=True)
+    fr = [(g * n_local, (g + 1) * n_local) for g in range(world)]
+    if world == 1:
+        bwd = fwd.T
+        br = fr
+    else:
+        # exact global in-degree of A^T rows (= out-degree histogram of sources), summed over ranks
+        cnt = torch.empty(n_glob, dtype=torch.int32, device=dev)
+        _lib.check(lib.ggad_col_histogram(_lib.ptr(fwd.col), fwd.nnz, _lib.ptr(cnt), n_glob, _lib.stream_ptr(dev)))
+        dist.all_reduce(cnt)
+        rowptr_t = torch.zeros(n_glob + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(cnt, 0, out=rowptr_t[1:])
+        br = gdist.nnz_balanced_ranges(rowptr_t.cpu().numpy(), world)
+        del cnt, rowptr_t
+        rs_all = torch.empty(n_glob, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(rs_all, fwd.row_scale)
+        lo, hi = br[rank]
+        bwd = synth.rmat_transposed_shard(n_local, m_local, world, args.seed, lo, hi, device=dev, col_scale=rs_all)
+    for g in (fwd, bwd):
+        g.plan
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t_build
+
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    x = torch.randn(n_glob, d, device=dev, generator=gen)
+    y_full = torch.empty(n_glob, d, device=dev)
+    dx_full = torch.empty(n_glob, d, device=dev)
+
+    def compute(g, inp):
+        return ops.gather_reduce(g, inp)["y"]
+
+    def step(ev=None):
+        y_loc = compute(fwd, x)
+        if ev:
+            ev[1].record()
+        if world > 1:
+            gdist.all_gather_rows(y_loc, fr, y_full)
+            yy = y_full
+        else:
+            yy = y_loc
+        if ev:
+            ev[2].record()
+        dx_loc = compute(bwd, yy)
+        if ev:
+            ev[3].record()
+        if world > 1:
+            gdist.all_gather_rows(dx_loc, br, dx_full)
+        return y_loc, dx_loc
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    launches0 = _lib.launch_count()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        evs[i][0].record()
+        step(evs[i])
+        evs[i][4].record()
+    t1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = t0.elapsed_time(t1)
+    tt = torch.tensor([total_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tt.item()) / args.steps
+    seg = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in evs])   # fwd, xchg, bwd, xchg
+    seg_mean = seg.mean(0)
+    total_edges = m_local * world
+    value = total_edges / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (forward gather) ----
+    peak, peak_src = hbm_peak()
+    b_alg = fwd.algorithmic_bytes(d)
+    fwd_s = seg_mean[0] * 1e-3
+    achieved = b_alg / fwd_s / 1e9
+    roofline = dict(bound="hbm", kernel="gather_tiled_kernel<16,1> (forward, + tile_fixup)", achieved=achieved, peak=peak,
+                    unit="GB/s", frac=achieved / peak, traffic=None, peak_source=peak_src,
+                    algorithmic_bytes=int(b_alg), fwd_ms=float(seg_mean[0]), bwd_ms=float(seg_mean[2]),
+                    fwd_edges_per_s=m_local / fwd_s,
+                    gather_bytes_model=int(fwd.nnz * (4 + 4 * d) + (fwd.n_rows + 1) * 8 + fwd.n_rows * d * 4))
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            tr = json.load(open(prof)).get(args.workload)
+            if tr:
+                roofline["traffic"] = tr["fwd_dram_bytes"]
+                roofline["traffic_source"] = tr.get("source")
+        except Exception:
+            pass
+
+    # ---- end-to-end: host buffers through the public entry points ----
+    e2e = None
+    if not args.no_e2e:
+        e2e = e2e_leg(args, world, rank, dev, fwd, bwd, fr, br, value)
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cn, cm = max(1000, n_local // args.cpu_frac), max(1000, m_local // args.cpu_frac)
+        cpu, _ = cpu_reference_leg(cn, cm, d, steps=2, warmup=1)
+
+    if rank == 0:
+        out = {
+            "metric": "edges/sec (SpMM fwd+bwd)", "value": value, "unit": "edges/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (R-MAT 0.57/0.19/0.19/0.05, on-device)",
+            "config": {"workload": args.workload, "nodes_per_gpu": n_local, "edges_per_gpu": m_local, "width": d,
+                       "global_nodes": n_glob, "global_edges": total_edges, "aggregation": "mean (row_scale = 1/deg)",
+                       "l2": "inputs larger than L2 (no flush)" if n_glob * d * 4 > 2e8 else "L2-resident operand (no flush)",
+                       "parallelism": f"dst-node-range x{world}, all-gather per pass", "graph_build_s": round(t_build, 2)},
+            "segments_ms": {"fwd_compute": float(seg_mean[0]), "fwd_exchange": float(seg_mean[1]),
+                            "bwd_compute": float(seg_mean[2]), "bwd_exchange": float(seg_mean[3])},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def e2e_leg(args, world, rank, dev, fwd, bwd, fr, br, value):
+    """Same pass with host-resident features: H2D of the rank's feature shard, D2H of its dX shard + loss."""
+    import ctypes as C
+    import torch.distributed as dist
+    from ggad_b200 import _lib, dist as gdist, ops
+    lib, ptr = _lib.lib(), _lib.ptr
+    d = args.width
+    n_local = args.nodes
+    n_glob = n_local * world
+    steps = max(2, min(args.steps, 5))
+    lo_b, hi_b = br[rank]
+    x_host = torch.randn(n_local, d).pin_memory()
+    dx_host = torch.empty(hi_b - lo_b, d).pin_memory()
+    h2d, d2h = x_host.numel() * 4, dx_host.numel() * 4 + 8
+    times = []
+    if world == 1:
+        def res(c):
+            r = _lib.ResidentCSR()
+            r.rowptr, r.col, r.val = ptr(c.rowptr), ptr(c.col), ptr(c.val)
+            r.row_scale, r.col_scale = ptr(c.row_scale), ptr(c.col_scale)
+            r.n_rows, r.n_cols, r.nnz = c.n_rows, c.n_cols, c.nnz
+            p = c.plan
+            r.tile_row, r.tile_edge, r.n_tiles = ptr(p[0]), ptr(p[1]), p[2]
+            return r
+        ra, rt = res(fwd), res(bwd)
+        bufs = [torch.empty(n_local, d, device=dev) for _ in range(3)]
+        ws = torch.empty(2 * max(ra.n_tiles, rt.n_tiles) * d + n_local + 16, device=dev)
+        loss = C.c_double(0)
+        for i in range(steps + 1):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            _lib.check(lib.ggad_spmm_fwd_bwd_host(C.byref(ra), C.byref(rt), ptr(x_host), None, ptr(dx_host),
+                                                  C.addressof(loss), d, ptr(bufs[0]), ptr(bufs[1]), ptr(bufs[2]), ptr(ws),
+                                                  _lib.stream_ptr(dev)))
+            if i:
+                times.append(time.perf_counter() - t0)
+        api = "ggad_spmm_fwd_bwd_host (C ABI, pinned host buffers)"
+    else:
+        x_full = torch.empty(n_glob, d, device=dev)
+        y_full = torch.empty(n_glob, d, device=dev)
+        x_loc = torch.empty(n_local, d, device=dev)
+        for i in range(steps + 1):
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            x_loc.copy_(x_host, non_blocking=True)
+            gdist.all_gather_rows(x_loc, fr, x_full)
+            r = ops.gather_reduce(fwd, x_full, want_sumsq=True)
+            gdist.all_gather_rows(r["y"], fr, y_full)
+            dx = ops.gather_reduce(bwd, y_full)["y"]
+            dx_host.copy_(dx, non_blocking=True)
+            loss = 0.5 * float(r["sumsq"].double().sum().item())
+            torch.cuda.synchronize()
+            if i:
+                times.append(time.perf_counter() - t0)
+        api = "ggad_b200.ops.gather_reduce + dist.all_gather_rows (pinned host shards)"
+    t = torch.tensor([float(np.mean(times))], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t.item())
+    return {"value": args.edges * world / sec, "unit": "edges/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "ms_per_step": sec * 1e3, "steps": steps, "api": api}
+
+
+def reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_local, m_local, d = args.nodes, args.edges, args.width
+    cn, cm = max(1000, n_local // args.cpu_frac), max(1000, m_local // args.cpu_frac)
+    cpu, t = cpu_reference_leg(cn, cm, d, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    out = {
+        "impl": "reference", "metric": "edges/sec (SpMM fwd+bwd)", "value": cpu["value"], "unit": "edges/s",
+        "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": max(1, min(args.warmup, 2)), "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (R-MAT 0.57/0.19/0.19/0.05, host numpy)",
+        "config": {"workload": args.workload, "nodes_per_gpu": n_local, "edges_per_gpu": m_local, "width": d,
+                   "sample": cpu["sample"]},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="S64", choices=list(WORKLOADS) + ["custom"])
+    ap.add_argument("--nodes", type=int, default=None)
+    ap.add_argument("--edges", type=int, default=None)
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-frac", type=int, default=8, help="CPU legs run on 1/frac of the per-GPU workload")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.workload != "custom":
+        n, m, d = WORKLOADS[args.workload]
+        args.nodes = args.nodes or n
+        args.edges = args.edges or m
+        args.width = args.width or d
+    if args.impl == "reference":
+        # keep the whole CPU run to a few minutes: shrink the sample as K grows (~4 s per step at 1/8 of S64)
+        args.cpu_frac *= max(1, -(-args.steps // 25))
+        reference(args)
+    else:
+        native(args)
+
+
+if __name__ == "__main__":
+    main()

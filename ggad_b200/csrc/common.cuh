@@ -48,8 +48,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
+  uint32_t spins = 0;
   const uint32_t addr = smem_u32(bar);
   do {
+    if (++spins > (1u << 26)) asm volatile("trap;");  // a lost TMA completion must not hang the GPU
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"

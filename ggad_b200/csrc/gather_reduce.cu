@@ -62,11 +62,23 @@ __device__ __forceinline__ unsigned group_mask() {
 }
 
 // Per-row epilogue; executed convergently by the G lanes of one group.
-template <int G, int CH>
+template <int G, int CH, bool FULL = true>
 __device__ __forceinline__ void finish_row(const GatherArgs& a, int64_t r, const float4 (&acc)[CH], int gl,
                                            unsigned gmask) {
   const int V = a.d >> 2;
   const float rs = a.row_scale ? __ldg(a.row_scale + r) : 1.f;
+  if (!FULL) {  // plain SpMM: y = row_scale * acc, nothing else requested
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const int ch = gl + G * j;
+      if (ch < V) {
+        float4 v = acc[j];
+        v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
+        stg_cs_f4(reinterpret_cast<float4*>(a.y + r * a.ldy) + ch, v);
+      }
+    }
+    return;
+  }
   const bool want_dot = a.dot_out != nullptr;
   const bool want_ss = a.sumsq != nullptr;
   const float4* dm = nullptr;
@@ -123,8 +135,8 @@ __device__ __forceinline__ void resolve_edge(const GatherArgs& a, int& c, float&
   if (GEN) {
     if (a.col_scale) w *= __ldg(a.col_scale + c);
     if (a.xmap) c = __ldg(a.xmap + c);
+    if (w == 0.f) c = -1;  // zero-scaled columns are skipped without touching x
   }
-  if (w == 0.f) c = -1;
 }
 
 // ---------------------------------------------------------------------------
@@ -210,8 +222,10 @@ struct TileSmem {
   static constexpr int kBytes = kPart + NGRP * 2 * G * CH * 16;
 };
 
-template <int G, int CH, bool GEN>
-__global__ void __launch_bounds__(kThreads, (CH <= 2) ? 3 : 2) gather_tiled_kernel(const GatherArgs a) {
+// MODE 0: unweighted (val == NULL), 1: per-edge val, 2: general (col_scale / xmap, optional val).
+// EPI false: plain y = row_scale * acc; true: bias / activation / z / sumsq / dot epilogue.
+template <int G, int CH, int MODE, bool EPI>
+__global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2)) gather_tiled_kernel(const GatherArgs a) {
   using L = TileSmem<G, CH>;
   constexpr int NGRP = L::NGRP;
   constexpr int U = (CH == 1) ? 8 : (CH == 2 ? 4 : 2);
@@ -295,8 +309,15 @@ __global__ void __launch_bounds__(kThreads, (CH <= 2) ? 3 : 2) gather_tiled_kern
     bool head_pending = ((i1 == 0) ? rstart0 : s_rend[i1 - 1]) < j1;  // first row began before this group
     int flag = 0;
     float4 acc[CH];
+    bool chok[CH];
 #pragma unroll
-    for (int j = 0; j < CH; ++j) acc[j] = f4_zero();
+    for (int j = 0; j < CH; ++j) {
+      acc[j] = f4_zero();
+      chok[j] = gl + G * j < V;
+    }
+    const float4* __restrict__ xb = x4 + gl;  // this lane's 16-byte chunk of every row
+    const int32_t* __restrict__ sc = s_col + lead;
+    const float* __restrict__ sv = s_val + lead;
 
     auto flush = [&]() {
       if (head_pending) {
@@ -305,40 +326,70 @@ __global__ void __launch_bounds__(kThreads, (CH <= 2) ? 3 : 2) gather_tiled_kern
         flag |= 1;
         head_pending = false;
       } else {
-        finish_row<G, CH>(a, r0 + row, acc, gl, gmask);
+        finish_row<G, CH, EPI>(a, r0 + row, acc, gl, gmask);
       }
 #pragma unroll
       for (int j = 0; j < CH; ++j) acc[j] = f4_zero();
       ++row;
       cur_end = s_rend[row];
     };
+    auto accumulate = [&](float w, const float4 (&v)[CH]) {
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        if (MODE == 0) f4_add(acc[j], v[j]);
+        else f4_fma(acc[j], w, v[j]);
+      }
+    };
 
-    for (int e = j1; e < j2; e += U) {
+    int e = j1;
+    // full batches of U edges: U independent 128-bit gathers per lane in flight
+    for (; e + U <= j2; e += U) {
       int c[U];
       float w[U];
       float4 xv[U][CH];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int ee = e + u;
-        const bool ok = ee < j2;
-        c[u] = ok ? s_col[lead + ee] : -1;
-        w[u] = ok ? (has_val ? s_val[lead + ee] : 1.f) : 0.f;
-        if (ok) resolve_edge<GEN>(a, c[u], w[u]);
+        c[u] = sc[e + u];
+        w[u] = (MODE == 0) ? 1.f : ((MODE == 1 || has_val) ? sv[e + u] : 1.f);
+        if (MODE == 2) resolve_edge<true>(a, c[u], w[u]);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int j = 0; j < CH; ++j) {
-          const int ch = gl + G * j;
-          xv[u][j] = (c[u] >= 0 && ch < V) ? ldg_f4(x4 + int64_t(c[u]) * ldx4 + ch) : f4_zero();
+        for (int j = 0; j < CH; ++j)
+          xv[u][j] = (chok[j] && (MODE < 2 || c[u] >= 0)) ? ldg_f4(xb + int64_t(c[u]) * ldx4 + G * j) : f4_zero();
+      if (e + U <= cur_end) {  // whole batch inside the current row: no boundary checks
+#pragma unroll
+        for (int u = 0; u < U; ++u) accumulate(w[u], xv[u]);
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          while (e + u >= cur_end) flush();
+          accumulate(w[u], xv[u]);
         }
+      }
+    }
+    if (e < j2) {  // ragged tail (< U edges)
+      int c[U];
+      float w[U];
+      float4 xv[U][CH];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int ee = e + u;
-        if (ee < j2) {
-          while (ee >= cur_end) flush();
+        const bool ok = e + u < j2;
+        c[u] = ok ? sc[e + u] : -1;
+        w[u] = ok ? ((MODE == 0) ? 1.f : ((MODE == 1 || has_val) ? sv[e + u] : 1.f)) : 0.f;
+        if (MODE == 2 && ok) resolve_edge<true>(a, c[u], w[u]);
+      }
 #pragma unroll
-          for (int j = 0; j < CH; ++j) f4_fma(acc[j], w[u], xv[u][j]);
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < CH; ++j)
+          xv[u][j] = (chok[j] && c[u] >= 0) ? ldg_f4(xb + int64_t(c[u]) * ldx4 + G * j) : f4_zero();
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (e + u < j2) {
+          while (e + u >= cur_end) flush();
+          accumulate(w[u], xv[u]);
         }
       }
     }
@@ -373,7 +424,7 @@ __global__ void __launch_bounds__(kThreads, (CH <= 2) ? 3 : 2) gather_tiled_kern
           for (int j = 0; j < CH; ++j)
             if (gl + G * j < V) reinterpret_cast<float4*>(ws_head)[gl + G * j] = chain[j];
         } else {
-          finish_row<G, CH>(a, r0 + row, chain, gl, gmask);
+          finish_row<G, CH, EPI>(a, r0 + row, chain, gl, gmask);
         }
 #pragma unroll
         for (int j = 0; j < CH; ++j) chain[j] = f4_zero();
@@ -391,7 +442,7 @@ __global__ void __launch_bounds__(kThreads, (CH <= 2) ? 3 : 2) gather_tiled_kern
 }
 
 // Finish rows that were cut by tile boundaries: one lane group per tile whose first row began earlier.
-template <int G, int CH>
+template <int G, int CH, bool EPI>
 __global__ void __launch_bounds__(kThreads) tile_fixup_kernel(const GatherArgs a) {
   const int64_t k = (int64_t(blockIdx.x) * kThreads + threadIdx.x) / G;
   if (k >= a.n_tiles) return;
@@ -416,52 +467,67 @@ __global__ void __launch_bounds__(kThreads) tile_fixup_kernel(const GatherArgs a
 #pragma unroll
   for (int j = 0; j < CH; ++j)
     if (gl + G * j < V) f4_add(acc[j], h[gl + G * j]);
-  finish_row<G, CH>(a, r0, acc, gl, gmask);
+  finish_row<G, CH, EPI>(a, r0, acc, gl, gmask);
 }
 
 // ---------------------------------------------------------------------------
 // host dispatch
 // ---------------------------------------------------------------------------
-template <int G, int CH, bool GEN>
-static int launch_variant(const GatherArgs& a, cudaStream_t st, int sm_count) {
-  if (a.n_rows == 0) return GGAD_OK;
-  if (a.tile_row) {
-    using L = TileSmem<G, CH>;
-    static bool attr_done = false;  // per instantiation
-    if (!attr_done) {
-      GGAD_CUDA_OK(cudaFuncSetAttribute(gather_tiled_kernel<G, CH, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        L::kBytes));
-      attr_done = true;
-    }
-    gather_tiled_kernel<G, CH, GEN><<<(unsigned)a.n_tiles, kThreads, L::kBytes, st>>>(a);
-    GGAD_CUDA_OK(cudaGetLastError());
-    const int64_t fix_blocks = (a.n_tiles * G + kThreads - 1) / kThreads;
-    tile_fixup_kernel<G, CH><<<(unsigned)fix_blocks, kThreads, 0, st>>>(a);
-    GGAD_CUDA_OK(cudaGetLastError());
-    count_launch(2);
-  } else {
-    const int64_t gpb = kThreads / G;
-    int64_t blocks = (a.n_rows + gpb - 1) / gpb;
-    const int64_t cap = int64_t(sm_count) * 64;
-    if (blocks > cap) blocks = cap;
-    gather_rows_kernel<G, CH, GEN><<<(unsigned)blocks, kThreads, 0, st>>>(a);
-    GGAD_CUDA_OK(cudaGetLastError());
-    count_launch(1);
+template <int G, int CH, int MODE, bool EPI>
+static int launch_tiled(const GatherArgs& a, cudaStream_t st) {
+  using L = TileSmem<G, CH>;
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    GGAD_CUDA_OK(cudaFuncSetAttribute(gather_tiled_kernel<G, CH, MODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      L::kBytes));
+    attr_done = true;
   }
+  gather_tiled_kernel<G, CH, MODE, EPI><<<(unsigned)a.n_tiles, kThreads, L::kBytes, st>>>(a);
+  GGAD_CUDA_OK(cudaGetLastError());
+  const int64_t fix_blocks = (a.n_tiles * G + kThreads - 1) / kThreads;
+  tile_fixup_kernel<G, CH, EPI><<<(unsigned)fix_blocks, kThreads, 0, st>>>(a);
+  GGAD_CUDA_OK(cudaGetLastError());
+  count_launch(2);
   return GGAD_OK;
 }
 
-template <bool GEN>
+template <int G, int CH>
+static int launch_variant(const GatherArgs& a, cudaStream_t st, int sm_count) {
+  if (a.n_rows == 0) return GGAD_OK;
+  const bool gen = a.xmap || a.col_scale;
+  if (a.tile_row) {
+    const bool epi = a.bias || a.prelu_slope || a.relu || a.z || a.sumsq || a.dot_out || !a.y;
+    const int mode = gen ? 2 : (a.val ? 1 : 0);
+    if (epi) {
+      if (mode == 0) return launch_tiled<G, CH, 0, true>(a, st);
+      if (mode == 1) return launch_tiled<G, CH, 1, true>(a, st);
+      return launch_tiled<G, CH, 2, true>(a, st);
+    }
+    if (mode == 0) return launch_tiled<G, CH, 0, false>(a, st);
+    if (mode == 1) return launch_tiled<G, CH, 1, false>(a, st);
+    return launch_tiled<G, CH, 2, false>(a, st);
+  }
+  const int64_t gpb = kThreads / G;
+  int64_t blocks = (a.n_rows + gpb - 1) / gpb;
+  const int64_t cap = int64_t(sm_count) * 64;
+  if (blocks > cap) blocks = cap;
+  if (gen) gather_rows_kernel<G, CH, true><<<(unsigned)blocks, kThreads, 0, st>>>(a);
+  else gather_rows_kernel<G, CH, false><<<(unsigned)blocks, kThreads, 0, st>>>(a);
+  GGAD_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return GGAD_OK;
+}
+
 static int dispatch_width(const GatherArgs& a, cudaStream_t st, int sm_count) {
   const int V = a.d >> 2;
-  if (V <= 4) return launch_variant<4, 1, GEN>(a, st, sm_count);
-  if (V <= 8) return launch_variant<8, 1, GEN>(a, st, sm_count);
-  if (V <= 16) return launch_variant<16, 1, GEN>(a, st, sm_count);
-  if (V <= 32) return launch_variant<32, 1, GEN>(a, st, sm_count);
-  if (V <= 64) return launch_variant<32, 2, GEN>(a, st, sm_count);
-  if (V <= 96) return launch_variant<32, 3, GEN>(a, st, sm_count);
-  if (V <= 128) return launch_variant<32, 4, GEN>(a, st, sm_count);
-  return launch_variant<32, 6, GEN>(a, st, sm_count);
+  if (V <= 4) return launch_variant<4, 1>(a, st, sm_count);
+  if (V <= 8) return launch_variant<8, 1>(a, st, sm_count);
+  if (V <= 16) return launch_variant<16, 1>(a, st, sm_count);
+  if (V <= 32) return launch_variant<32, 1>(a, st, sm_count);
+  if (V <= 64) return launch_variant<32, 2>(a, st, sm_count);
+  if (V <= 96) return launch_variant<32, 3>(a, st, sm_count);
+  if (V <= 128) return launch_variant<32, 4>(a, st, sm_count);
+  return launch_variant<32, 6>(a, st, sm_count);
 }
 
 int sm_count_cached();  // api.cu
@@ -502,8 +568,7 @@ int gather_reduce_impl(const ggad_gather_desc_t* d, cudaStream_t st) {
   a.tile_row = d->tile_row; a.tile_edge = d->tile_edge; a.n_tiles = d->n_tiles; a.ws = d->ws;
   const int sms = sm_count_cached();
   if (sms <= 0) return GGAD_ERR_CUDA;
-  if (a.xmap || a.col_scale) return dispatch_width<true>(a, st, sms);
-  return dispatch_width<false>(a, st, sms);
+  return dispatch_width(a, st, sms);
 }
 
 int plan_build_impl(const int64_t* rowptr, int64_t n_rows, int64_t nnz, int32_t* tile_row, int64_t* tile_edge,

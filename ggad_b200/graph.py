@@ -131,6 +131,7 @@ class CSRGraph:
                     check(lib().ggad_csr_transpose(ptr(self.rowptr), ptr(self.col), ptr(self.val), self.n_rows, self.n_cols,
                                                    self.nnz, ptr(rpt), ptr(ct), ptr(vt), None, stream_ptr(self.device)))
                 t = CSRGraph(rpt, ct, vt, self.n_cols, self.n_rows, row_scale=self.col_scale, col_scale=self.row_scale)
+                t = t.fold_col_scale()
             t._T = self
             self._T = t
         return self._T
@@ -156,6 +157,19 @@ class CSRGraph:
             if len(self._rows_cache) > 8:
                 self._rows_cache.clear()
             self._rows_cache[key] = g
+        return g
+
+    def fold_col_scale(self) -> "CSRGraph":
+        """Same operator with the column scale folded into per-edge values (val[e] *= col_scale[col[e]]).
+        A streamed 4 B/edge value is far cheaper than a random 4 B gather (one 32 B sector) per edge."""
+        if self.col_scale is None:
+            return self
+        v = self.col_scale[self.col.long()]
+        if self.val is not None:
+            v = v * self.val
+        g = CSRGraph(self.rowptr, self.col, v.contiguous(), self.n_rows, self.n_cols, row_scale=self.row_scale,
+                     col_scale=None, symmetric_pattern=False, use_plan=self._use_plan)
+        g._plan = self._plan
         return g
 
     def degrees(self) -> torch.Tensor:

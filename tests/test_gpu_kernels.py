@@ -271,7 +271,12 @@ def test_rmat_generator_and_shards():
     lo, hi = 3000, 9000
     t = synth.rmat_transposed_shard(n_local, n_edges, shards, 7, lo, hi)
     sub = full_t[lo:hi]
-    assert np.array_equal(t.rowptr.cpu().numpy(), sub.indptr.astype(np.int64))
+    ref_ptr = np.zeros(hi - lo + 1, np.int64)                      # multigraph: duplicates are kept, count them
+    np.cumsum(np.bincount(cols[(cols >= lo) & (cols < hi)] - lo, minlength=hi - lo), out=ref_ptr[1:])
+    assert np.array_equal(t.rowptr.cpu().numpy(), ref_ptr)
+    sel = (cols >= lo) & (cols < hi)
+    order = np.lexsort((rows[sel], cols[sel]))
+    assert np.array_equal(t.col.cpu().numpy(), rows[sel][order].astype(np.int32))
     x = np.random.default_rng(0).standard_normal((n_local * shards, 8)).astype(np.float32)
     ref = torch.from_numpy(sub @ x)
     assert_close(ops.gather_reduce(t, torch.from_numpy(x).cuda())["y"], ref, atol=1e-4, what="transposed shard")

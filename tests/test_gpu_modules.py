@@ -163,7 +163,7 @@ def test_two_layer_sage_stack_callable_features():
     agg2 = gs.MeanAggregator(lambda nodes: enc1(nodes.tolist()).t(), cuda=True)
     enc2 = gs.Encoder(lambda nodes: enc1(nodes.tolist()).t(), h, h, adj, agg2, num_sample=None, base_model=enc1,
                       gcn=False, cuda=True)
-    enc2 = enc2.cuda()
+    enc2 = enc2.to("cuda")        # (.cuda is shadowed by the reference's bool attribute of the same name)
     nodes = list(range(0, 60, 2))
     out = enc2(nodes)
     out.sum().backward()
