@@ -5,8 +5,9 @@
 
 Workload (config.workload): ``S64`` = one C5 shard per GPU -- 6.25 M nodes / 125 M edges / d = 64 per GPU
 (at N = 8 this is BASELINE.json's 50 M-node / 1 B-edge graph) -- weak scaling.  A step is
-    Y  = A[lo:hi, :] X          (mean aggregation over the rank's destination range)   + all-gather(Y)
-    dX = A^T[lo':hi', :] dY     (dY = Y, loss = |Y|^2/2; transposed CSR, no atomics)   + all-gather(dX)
+    Y  = A[lo:hi, :] X          (mean aggregation over the rank's destination range), replicated to all ranks
+                                (N>1: NVLink P2P stores fused into the gather epilogue, or NCCL all-gather)
+    dX[lo':hi'] = A^T[lo':hi', :] dY   (dY = Y, loss = |Y|^2/2; transposed CSR rows, no atomics; stays sharded)
 `value` = total edges of all ranks / step time with everything resident in HBM (inputs >> L2, so no flush
 is needed); `e2e` = same pass with the features coming from pinned host memory and dX + loss read back,
 through the C-ABI host entry point (ggad_spmm_fwd_bwd_host) at N = 1.  `roofline` is for the forward
@@ -162,6 +163,8 @@ def native(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     n_local, m_local, d = args.nodes, args.edges, args.width
     n_glob = n_local * world
@@ -169,7 +172,8 @@ def native(args):
 
     # ---- graph shards (generated on device) ----
     t_build = time.perf_counter()
-    fwd = synth.rmat_shard(n_local, m_local, world, rank, seed=args.seed, device=dev, mean=True)
+    abc = tuple(float(t) for t in args.rmat.split(",")) if args.rmat else None
+    fwd = synth.rmat_shard(n_local, m_local, world, rank, seed=args.seed, device=dev, mean=True, abc=abc)
     fr = [(g * n_local, (g + 1) * n_local) for g in range(world)]
     if world == 1:
         bwd = fwd.T
@@ -186,7 +190,8 @@ def native(args):
         rs_all = torch.empty(n_glob, dtype=torch.float32, device=dev)
         dist.all_gather_into_tensor(rs_all, fwd.row_scale)
         lo, hi = br[rank]
-        bwd = synth.rmat_transposed_shard(n_local, m_local, world, args.seed, lo, hi, device=dev, col_scale=rs_all)
+        bwd = synth.rmat_transposed_shard(n_local, m_local, world, args.seed, lo, hi, device=dev, col_scale=rs_all,
+                                          abc=abc).fold_col_scale()
     for g in (fwd, bwd):
         g.plan
     torch.cuda.synchronize()
@@ -194,29 +199,55 @@ def native(args):
 
     gen = torch.Generator(device=dev).manual_seed(1234)
     x = torch.randn(n_glob, d, device=dev, generator=gen)
-    y_full = torch.empty(n_glob, d, device=dev)
-    dx_full = torch.empty(n_glob, d, device=dev)
+    y_full = torch.empty(n_glob, d, device=dev) if (world > 1 and args.exchange == "nccl") else None
 
     def compute(g, inp):
         return ops.gather_reduce(g, inp)["y"]
 
+    # exchange of the forward output (= dY of the backward): fused into the gather epilogue over NVLink
+    # peer memory (P2P stores or NVSwitch multicast), or a plain NCCL all-gather
+    exchange = args.exchange if world > 1 else "none"
+    rep = None
+    if exchange in ("fused", "multicast"):
+        try:
+            rep = gdist.PeerReplica(n_glob, d, fr, rank, dev)
+            if exchange == "multicast" and not rep.multicast_ptr:
+                exchange = "fused"
+        except Exception as e:          # symmetric memory unavailable: fall back to the NCCL collective
+            if rank == 0:
+                print(f"[bench] symmetric memory unavailable ({e}); using NCCL all-gather", file=sys.stderr)
+            exchange, rep = "nccl", None
+
     def step(ev=None):
-        y_loc = compute(fwd, x)
-        if ev:
-            ev[1].record()
-        if world > 1:
+        if exchange == "none":
+            yy = compute(fwd, x)
+            if ev:
+                ev[1].record()
+                ev[2].record()
+        elif exchange == "nccl":
+            y_loc = compute(fwd, x)
+            if ev:
+                ev[1].record()
             gdist.all_gather_rows(y_loc, fr, y_full)
             yy = y_full
+            if ev:
+                ev[2].record()
         else:
-            yy = y_loc
-        if ev:
-            ev[2].record()
-        dx_loc = compute(bwd, yy)
+            rep.barrier(0)                       # peers finished reading the previous Y
+            if exchange == "multicast":
+                ops.gather_reduce(fwd, x, y_out=rep.local_rows, y_multicast=rep.multicast_row_ptr)
+            else:
+                ops.gather_reduce(fwd, x, y_out=rep.local_rows, y_peers=rep.peer_row_ptrs)
+            if ev:
+                ev[1].record()
+            rep.barrier(1)                       # every shard has landed in every replica
+            yy = rep.buf
+            if ev:
+                ev[2].record()
+        dx_loc = compute(bwd, yy)                # dX stays sharded by source range (consumed per node)
         if ev:
             ev[3].record()
-        if world > 1:
-            gdist.all_gather_rows(dx_loc, br, dx_full)
-        return y_loc, dx_loc
+        return yy, dx_loc
 
     def barrier():
         if world > 1:
@@ -288,11 +319,11 @@ def native(args):
         out = {
             "metric": "edges/sec (SpMM fwd+bwd)", "value": value, "unit": "edges/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (R-MAT 0.57/0.19/0.19/0.05, on-device)",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (R-MAT %s, on-device)" % (args.rmat or "0.57/0.19/0.19/0.05"),
             "config": {"workload": args.workload, "nodes_per_gpu": n_local, "edges_per_gpu": m_local, "width": d,
                        "global_nodes": n_glob, "global_edges": total_edges, "aggregation": "mean (row_scale = 1/deg)",
                        "l2": "inputs larger than L2 (no flush)" if n_glob * d * 4 > 2e8 else "L2-resident operand (no flush)",
-                       "parallelism": f"dst-node-range x{world}, all-gather per pass", "graph_build_s": round(t_build, 2)},
+                       "parallelism": f"dst-node-range x{world}, exchange={exchange}", "graph_build_s": round(t_build, 2)},
             "segments_ms": {"fwd_compute": float(seg_mean[0]), "fwd_exchange": float(seg_mean[1]),
                             "bwd_compute": float(seg_mean[2]), "bwd_exchange": float(seg_mean[3])},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -398,7 +429,10 @@ def main():
     ap.add_argument("--edges", type=int, default=None)
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--rmat", default=None, help="a,b,c of the R-MAT generator (default 0.57,0.19,0.19); 0.25,0.25,0.25 = uniform")
     ap.add_argument("--cpu-frac", type=int, default=8, help="CPU legs run on 1/frac of the per-GPU workload")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "multicast", "nccl"],
+                    help="N>1: how the forward output is replicated (fused = NVLink P2P stores from the gather epilogue)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -48,6 +48,9 @@ struct GatherArgs {
   const int64_t* tile_edge;
   int64_t n_tiles;
   float* ws;
+  float* y_peer[7];
+  int n_peer;
+  float* y_mc;
 };
 
 constexpr int kThreads = 256;
@@ -59,6 +62,19 @@ __device__ __forceinline__ unsigned group_mask() {
   if (G == 32) return 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u;
   return ((1u << G) - 1u) << ((lane / G) * G);
+}
+
+// Store one finished 16-byte chunk of y: local copy, NVLink P2P copies into the peers' replicated
+// matrices, or a single NVSwitch multicast store (multimem.st) that lands on every rank.
+__device__ __forceinline__ void store_y(const GatherArgs& a, int64_t r, int ch, const float4& v) {
+  const int64_t off = r * a.ldy + int64_t(ch) * 4;
+  if (a.y) stg_cs_f4(reinterpret_cast<float4*>(a.y + off), v);
+  for (int p = 0; p < a.n_peer; ++p) stg_cs_f4(reinterpret_cast<float4*>(a.y_peer[p] + off), v);
+  if (a.y_mc) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.y_mc + off), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+  }
 }
 
 // Per-row epilogue; executed convergently by the G lanes of one group.
@@ -74,7 +90,7 @@ __device__ __forceinline__ void finish_row(const GatherArgs& a, int64_t r, const
       if (ch < V) {
         float4 v = acc[j];
         v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
-        stg_cs_f4(reinterpret_cast<float4*>(a.y + r * a.ldy) + ch, v);
+        store_y(a, r, ch, v);
       }
     }
     return;
@@ -108,7 +124,7 @@ __device__ __forceinline__ void finish_row(const GatherArgs& a, int64_t r, const
       } else if (a.relu) {
         v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
       }
-      if (a.y) stg_cs_f4(reinterpret_cast<float4*>(a.y + r * a.ldy) + ch, v);
+      store_y(a, r, ch, v);
       if (want_ss) ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
       if (want_dot) {
         const float4 m = __ldg(dm + ch);
@@ -298,8 +314,6 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
   const int g = tid / G, gl = tid % G;
   const unsigned gmask = group_mask<G>();
   const int V = a.d >> 2;
-  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(a.x);
-  const int64_t ldx4 = a.ldx >> 2;
   float4* my_part = s_part + (g * 2) * (G * CH);
 
   {
@@ -309,13 +323,20 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
     bool head_pending = ((i1 == 0) ? rstart0 : s_rend[i1 - 1]) < j1;  // first row began before this group
     int flag = 0;
     float4 acc[CH];
-    bool chok[CH];
+    // Byte offset of this lane's 16-byte chunk(s) inside a row.  Lanes beyond the row width (V not a
+    // multiple of G) re-read chunk 0: their sums are never stored, and no predicate is needed in the loop.
+    const char* lane_base[CH];
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       acc[j] = f4_zero();
-      chok[j] = gl + G * j < V;
+      lane_base[j] = reinterpret_cast<const char*>(a.x) + ((gl + G * j < V) ? uint32_t(gl + G * j) * 16u : 0u);
+      asm volatile("" : "+l"(lane_base[j]));  // keep it one opaque 64-bit register pair (IMAD.WIDE addend)
     }
-    const float4* __restrict__ xb = x4 + gl;  // this lane's 16-byte chunk of every row
+    const uint32_t row_bytes = uint32_t(a.ldx) * 4u;
+    // one IMAD.WIDE.U32 per gathered chunk: (x + lane offset) + col * row_bytes
+    auto load_chunk = [&](int c, int j) {
+      return ldg_f4(reinterpret_cast<const float4*>(lane_base[j] + uint64_t(uint32_t(c)) * row_bytes));
+    };
     const int32_t* __restrict__ sc = s_col + lead;
     const float* __restrict__ sv = s_val + lead;
 
@@ -356,8 +377,7 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int j = 0; j < CH; ++j)
-          xv[u][j] = (chok[j] && (MODE < 2 || c[u] >= 0)) ? ldg_f4(xb + int64_t(c[u]) * ldx4 + G * j) : f4_zero();
+        for (int j = 0; j < CH; ++j) xv[u][j] = (MODE < 2 || c[u] >= 0) ? load_chunk(c[u], j) : f4_zero();
       if (e + U <= cur_end) {  // whole batch inside the current row: no boundary checks
 #pragma unroll
         for (int u = 0; u < U; ++u) accumulate(w[u], xv[u]);
@@ -383,8 +403,7 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int j = 0; j < CH; ++j)
-          xv[u][j] = (chok[j] && c[u] >= 0) ? ldg_f4(xb + int64_t(c[u]) * ldx4 + G * j) : f4_zero();
+        for (int j = 0; j < CH; ++j) xv[u][j] = (c[u] >= 0) ? load_chunk(c[u], j) : f4_zero();
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (e + u < j2) {
@@ -496,7 +515,7 @@ static int launch_variant(const GatherArgs& a, cudaStream_t st, int sm_count) {
   if (a.n_rows == 0) return GGAD_OK;
   const bool gen = a.xmap || a.col_scale;
   if (a.tile_row) {
-    const bool epi = a.bias || a.prelu_slope || a.relu || a.z || a.sumsq || a.dot_out || !a.y;
+    const bool epi = a.bias || a.prelu_slope || a.relu || a.z || a.sumsq || a.dot_out || (!a.y && !a.y_mc);
     const int mode = gen ? 2 : (a.val ? 1 : 0);
     if (epi) {
       if (mode == 0) return launch_tiled<G, CH, 0, true>(a, st);
@@ -542,8 +561,8 @@ int gather_reduce_impl(const ggad_gather_desc_t* d, cudaStream_t st) {
   GGAD_REQUIRE(d->d <= GGAD_MAX_WIDTH, GGAD_ERR_UNSUPPORTED, "gather_reduce: width d=%d > %d", d->d, GGAD_MAX_WIDTH);
   GGAD_REQUIRE(d->ldx % 4 == 0 && d->ldx >= d->d, GGAD_ERR_ALIGN, "gather_reduce: ldx=%lld must be >= d and a multiple of 4", (long long)d->ldx);
   GGAD_REQUIRE(aligned16(d->x), GGAD_ERR_ALIGN, "gather_reduce: x not 16-byte aligned");
-  GGAD_REQUIRE(d->y || d->z || d->dot_out || d->sumsq, GGAD_ERR_INVALID, "gather_reduce: no output requested");
-  if (d->y || d->z) {
+  GGAD_REQUIRE(d->y || d->z || d->dot_out || d->sumsq || d->y_multicast, GGAD_ERR_INVALID, "gather_reduce: no output requested");
+  if (d->y || d->z || d->y_multicast) {
     GGAD_REQUIRE(d->ldy % 4 == 0 && d->ldy >= d->d, GGAD_ERR_ALIGN, "gather_reduce: ldy=%lld must be >= d and a multiple of 4", (long long)d->ldy);
     GGAD_REQUIRE(aligned16(d->y) && aligned16(d->z), GGAD_ERR_ALIGN, "gather_reduce: y/z not 16-byte aligned");
   }
@@ -566,6 +585,14 @@ int gather_reduce_impl(const ggad_gather_desc_t* d, cudaStream_t st) {
   a.y = d->y; a.z = d->z; a.ldy = d->ldy; a.sumsq = d->sumsq;
   a.dot_mat = d->dot_mat; a.lddot = d->lddot; a.dot_rows = d->dot_rows; a.dot_scale = d->dot_scale; a.dot_out = d->dot_out;
   a.tile_row = d->tile_row; a.tile_edge = d->tile_edge; a.n_tiles = d->n_tiles; a.ws = d->ws;
+  GGAD_REQUIRE(d->n_peer >= 0 && d->n_peer <= 7, GGAD_ERR_INVALID, "gather_reduce: n_peer must be in [0, 7]");
+  a.n_peer = d->n_peer;
+  for (int p = 0; p < 7; ++p) {
+    a.y_peer[p] = p < d->n_peer ? d->y_peer[p] : nullptr;
+    GGAD_REQUIRE(p >= d->n_peer || (a.y_peer[p] && aligned16(a.y_peer[p])), GGAD_ERR_ALIGN, "gather_reduce: y_peer[%d] null or unaligned", p);
+  }
+  a.y_mc = d->y_multicast;
+  GGAD_REQUIRE(aligned16(a.y_mc), GGAD_ERR_ALIGN, "gather_reduce: y_multicast not 16-byte aligned");
   const int sms = sm_count_cached();
   if (sms <= 0) return GGAD_ERR_CUDA;
   return dispatch_width(a, st, sms);

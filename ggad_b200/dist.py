@@ -76,6 +76,44 @@ def all_gather_rows(local: torch.Tensor, ranges: Sequence[Tuple[int, int]], out:
     return out
 
 
+class PeerReplica:
+    """A replicated [N, d] fp32 matrix in CUDA symmetric memory (one copy per rank, peer-mapped over NVLink).
+
+    Used for the *fused* exchange: the gather kernel's epilogue stores every finished row of the rank's
+    shard into all replicas (``y_peers``: P2P stores) or once to the NVSwitch multicast address
+    (``multicast``: multimem.st), so the all-gather is overlapped with the gather itself and no separate
+    collective is launched.  ``barrier()`` (device-side, on the current stream) orders writers and readers."""
+
+    def __init__(self, n_rows: int, d: int, ranges: Sequence[Tuple[int, int]], rank: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.ranges, self.d = rank, list(ranges), d
+        self.buf = symm.empty((n_rows, d), dtype=torch.float32, device=device)
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        try:
+            self.multicast_ptr = int(self.hdl.multicast_ptr)
+        except Exception:
+            self.multicast_ptr = 0
+
+    @property
+    def local_rows(self) -> torch.Tensor:
+        lo, hi = self.ranges[self.rank]
+        return self.buf[lo:hi]
+
+    @property
+    def peer_row_ptrs(self) -> List[int]:
+        lo, _ = self.ranges[self.rank]
+        return [p + lo * self.d * 4 for r, p in enumerate(self.ptrs) if r != self.rank]
+
+    @property
+    def multicast_row_ptr(self) -> int:
+        lo, _ = self.ranges[self.rank]
+        return self.multicast_ptr + lo * self.d * 4 if self.multicast_ptr else 0
+
+    def barrier(self, channel: int = 0) -> None:
+        self.hdl.barrier(channel=channel)
+
+
 class ShardedLayerPass:
     """Forward + backward of one aggregation layer on a node-range-sharded graph.
 

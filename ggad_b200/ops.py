@@ -34,7 +34,8 @@ def gather_reduce(g: CSRGraph, x: torch.Tensor, *, xmap: Optional[torch.Tensor] 
                   bias: Optional[torch.Tensor] = None, prelu_slope: Optional[torch.Tensor] = None, relu: bool = False,
                   want_y: bool = True, want_z: bool = False, want_sumsq: bool = False,
                   dot_mat: Optional[torch.Tensor] = None, dot_rows: Optional[torch.Tensor] = None,
-                  dot_scale: Optional[torch.Tensor] = None, use_graph_scales: bool = True):
+                  dot_scale: Optional[torch.Tensor] = None, use_graph_scales: bool = True,
+                  y_out: Optional[torch.Tensor] = None, y_peers=None, y_multicast: Optional[int] = None):
     """Raw (non-autograd) call of ggad_gather_reduce.  ``x`` is [n_x_rows, d] fp32 CUDA with d % 4 == 0.
     Returns dict(y=, z=, sumsq=, dot=) with the requested outputs."""
     _lib.require_cuda(x, "x")
@@ -48,7 +49,9 @@ def gather_reduce(g: CSRGraph, x: torch.Tensor, *, xmap: Optional[torch.Tensor] 
     if use_graph_scales:
         row_scale = g.row_scale if row_scale is None else row_scale
         col_scale = g.col_scale if col_scale is None else col_scale
-    y = torch.empty(n, d, dtype=torch.float32, device=dev) if want_y else None
+    if y_out is not None:
+        assert y_out.shape == (n, d) and y_out.dtype == torch.float32 and y_out.stride(0) == d and y_out.is_cuda
+    y = (y_out if y_out is not None else torch.empty(n, d, dtype=torch.float32, device=dev)) if want_y else None
     z = torch.empty(n, d, dtype=torch.float32, device=dev) if want_z else None
     ss = torch.empty(n, dtype=torch.float32, device=dev) if want_sumsq else None
     dot = torch.empty(n, dtype=torch.float32, device=dev) if dot_mat is not None else None
@@ -65,6 +68,14 @@ def gather_reduce(g: CSRGraph, x: torch.Tensor, *, xmap: Optional[torch.Tensor] 
         assert dot_mat.stride(1) == 1
         desc.dot_mat, desc.lddot = ptr(dot_mat), dot_mat.stride(0)
         desc.dot_rows, desc.dot_scale, desc.dot_out = ptr(dot_rows), ptr(dot_scale), ptr(dot)
+    if y_peers:                       # fused exchange: epilogue also stores into the peers' replicas
+        assert len(y_peers) <= 7
+        for i, pp in enumerate(y_peers):
+            desc.y_peer[i] = int(pp)
+        desc.n_peer = len(y_peers)
+    if y_multicast:
+        desc.y_multicast = int(y_multicast)
+        desc.y = None
     plan = g.plan
     if plan is not None:
         ws = g.workspace(d)

@@ -34,13 +34,13 @@ def _keys_to_csr(keys: torch.Tensor, n_keys: int, n_rows: int, n_cols: int, row_
 
 
 def rmat_shard(n_local: int, n_edges: int, n_shards: int = 1, shard: int = 0, seed: int = 0, device="cuda",
-               mean: bool = True) -> CSRGraph:
+               mean: bool = True, abc=None) -> CSRGraph:
     """Destination shard ``shard``: rows = its n_local destination nodes, columns = all n_shards*n_local
     source nodes.  With ``mean`` the operator is the GraphSAGE mean aggregator (row_scale = 1/deg from
     exact integer degrees; empty rows give 0)."""
     device = torch.device(device)
     keys = torch.empty(n_edges, dtype=torch.int64, device=device)
-    a, b, c = RMAT_ABC
+    a, b, c = abc or RMAT_ABC
     with torch.cuda.device(device):
         check(lib().ggad_rmat_keys(ptr(keys), n_edges, n_local, n_shards, shard, seed, a, b, c, 0, 0, None,
                                    stream_ptr(device)))
@@ -54,12 +54,12 @@ def rmat_shard(n_local: int, n_edges: int, n_shards: int = 1, shard: int = 0, se
 
 
 def rmat_transposed_shard(n_local: int, n_edges: int, n_shards: int, seed: int, lo: int, hi: int, device="cuda",
-                          col_scale: Optional[torch.Tensor] = None) -> CSRGraph:
+                          col_scale: Optional[torch.Tensor] = None, abc=None) -> CSRGraph:
     """Rows [lo, hi) of the TRANSPOSE of the whole n_shards-shard graph (rows = source nodes, columns =
     global destination ids), rebuilt by regenerating every shard's edges and keeping those whose source
     falls in the range.  ``col_scale`` (global, [n_shards*n_local]) carries the forward row scale."""
     device = torch.device(device)
-    a, b, c = RMAT_ABC
+    a, b, c = abc or RMAT_ABC
     scratch = torch.empty(n_edges, dtype=torch.int64, device=device)
     parts = []
     n_out = C.c_int64(0)

@@ -109,6 +109,15 @@ typedef struct ggad_gather_desc {
   const int64_t* tile_edge; /* [n_tiles + 1] */
   int64_t n_tiles;
   float* ws; /* [2 * n_tiles * d] partial-row workspace */
+  /* fused exchange (multi-GPU): every finished row of y is ALSO stored to these peer-mapped buffers
+   * (NVLink P2P stores from the epilogue, e.g. torch symmetric memory), or once to an NVSwitch
+   * multicast address (multimem.st).  Pointers address row 0 of THIS launch's rows inside the
+   * replicated [N, ldy] matrix of each peer; same ldy as y.  The caller synchronises the ranks
+   * (barrier) before anyone reads the replicated matrix. */
+  float* y_peer[7];
+  int32_t n_peer;
+  int32_t reserved;
+  float* y_multicast; /* NULL or multicast address covering all ranks (replaces y and y_peer) */
 } ggad_gather_desc_t;
 
 GGAD_API int ggad_gather_reduce(const ggad_gather_desc_t* desc, ggad_stream_t stream);

@@ -62,7 +62,7 @@ def test_struct_layout_matches_header():
             if not decl:
                 continue
             for part in decl.split(","):
-                names.append(re.findall(r"(\w+)\s*$", part.strip())[0])
+                names.append(re.findall(r"(\w+)\s*(?:\[\d+\])?\s*$", part.strip())[0])
         return names
     assert fields("ggad_gather_desc") == [f[0] for f in _lib.GatherDesc._fields_]
     assert fields("ggad_resident_csr") == [f[0] for f in _lib.ResidentCSR._fields_]
