@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libggad_b200.so")
+LIB_PATH = os.environ.get("GGAD_B200_LIB") or os.path.join(_HERE, "libggad_b200.so")
 
 GGAD_TILE_ITEMS = 2048
 GGAD_MAX_WIDTH = 768

@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libggad_b200.so")
-SOURCES = ["gather_reduce.cu", "graph_prep.cu", "api.cu"]
+SOURCES = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
@@ -36,16 +36,20 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build_library(force: bool = False, verbose: bool = False, out: str = None, defines=()) -> str:
+    """Compile csrc/*.cu and link the shared library.  ``out`` / ``defines`` build an experimental variant
+    (e.g. for A/B runs selected with the GGAD_B200_LIB environment variable)."""
+    global LIB
+    variant = out is not None
+    if not variant and not force and not _stale():
         return LIB
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if not variant else "build_" + os.path.basename(out).replace(".so", ""))
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *["-D" + d for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd += ["-Xptxas", "-v"]
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -56,14 +60,18 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
                 f.write(r.stderr)
         return obj
 
-    with ThreadPoolExecutor(len(SOURCES)) as ex:
+    with ThreadPoolExecutor(min(len(SOURCES), os.cpu_count() or 4)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-cudart", "static"]
+    target = out if variant else LIB
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", target, *objs, "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    return LIB
+    return target
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--out=")]
+    print(build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv, out=outs[0] if outs else None,
+                        defines=defs))

@@ -1,204 +1,28 @@
-// CSR neighbor gather-reduce with fused per-row epilogue (K1/K2/K3/K5 of DESIGN.md).
-//
-// Two kernels share one descriptor (ggad_gather_desc_t, include/ggad_b200.h):
-//
-//  * gather_tiled_kernel  -- the hot kernel.  Merge-path decomposition: a CTA owns a tile of
-//    GGAD_TILE_ITEMS consecutive (row-end | edge) items of the CSR, so work per CTA is constant
-//    whatever the degree distribution (power-law hubs are split, empty rows cost one item).
-//    The tile's col/val slice is staged into shared memory with ONE TMA bulk copy
-//    (cp.async.bulk + mbarrier complete_tx); row ends are staged as int32 offsets.  The tile is
-//    then split evenly (second-level merge path) over lane groups of G lanes; a group walks its
-//    items in order, keeping U neighbor rows (128-bit ld.global.nc per lane) in flight, and
-//    finishes rows that lie entirely inside its range directly from registers (scale, bias,
-//    PReLU/ReLU, |y|^2, dot epilogue).  Rows cut by a group boundary are combined through
-//    shared memory in group order; rows cut by a tile boundary go through a small global
-//    workspace and tile_fixup_kernel -- fixed summation order, no float atomics.
-//
-//  * gather_rows_kernel   -- one lane group per row; used when no plan is supplied.
-//
-// Roofline: HBM-bound (<= 0.5 flop/B).  Algorithmic bytes per launch
-//   nnz*(4 + 4*[val]) + (n_rows+1)*8 + n_x_rows*d*4 + n_rows*d*4      
-#include "common.cuh"
+// Host side of ggad_gather_reduce / ggad_plan_build: validation and dispatch on the row width.
+// The kernels live in gather_kernels.cuh and are instantiated per width class in gather_inst_*.cu.
+#include "gather_kernels.cuh"
 
 namespace ggad {
 
-struct GatherArgs {
-  const int64_t* rowptr;
-  const int32_t* col;
-  const float* val;
-  int64_t n_rows, nnz;
-  const float* x;
-  int64_t ldx;
-  const int32_t* xmap;
-  const float* col_scale;
-  const float* row_scale;
-  int32_t d, relu;
-  const float* bias;
-  const float* prelu_slope;
-  float* y;
-  float* z;
-  int64_t ldy;
-  float* sumsq;
-  const float* dot_mat;
-  int64_t lddot;
-  const int32_t* dot_rows;
-  const float* dot_scale;
-  float* dot_out;
-  const int32_t* tile_row;
-  const int64_t* tile_edge;
-  int64_t n_tiles;
-  float* ws;
-  float* y_peer[7];
-  int n_peer;
-  float* y_mc;
-};
+int launch_g4c1(const GatherArgs& a, cudaStream_t st, int sm_count);
+int launch_g8c1(const GatherArgs& a, cudaStream_t st, int sm_count);
+int launch_g16c1(const GatherArgs& a, cudaStream_t st, int sm_count);
+int launch_g32c1(const GatherArgs& a, cudaStream_t st, int sm_count);
+int launch_g32c2(const GatherArgs& a, cudaStream_t st, int sm_count);
+int launch_g32c3(const GatherArgs& a, cudaStream_t st, int sm_count);
+int launch_g32c4(const GatherArgs& a, cudaStream_t st, int sm_count);
+int launch_g32c6(const GatherArgs& a, cudaStream_t st, int sm_count);
 
-constexpr int kThreads = 256;
-constexpr int kTile = GGAD_TILE_ITEMS;
-constexpr int kBig = 0x3fffffff;
-
-template <int G>
-__device__ __forceinline__ unsigned group_mask() {
-  if (G == 32) return 0xffffffffu;
-  const unsigned lane = threadIdx.x & 31u;
-  return ((1u << G) - 1u) << ((lane / G) * G);
-}
-
-// Store one finished 16-byte chunk of y: local copy, NVLink P2P copies into the peers' replicated
-// matrices, or a single NVSwitch multicast store (multimem.st) that lands on every rank.
-__device__ __forceinline__ void store_y(const GatherArgs& a, int64_t r, int ch, const float4& v) {
-  const int64_t off = r * a.ldy + int64_t(ch) * 4;
-  if (a.y) stg_cs_f4(reinterpret_cast<float4*>(a.y + off), v);
-  for (int p = 0; p < a.n_peer; ++p) stg_cs_f4(reinterpret_cast<float4*>(a.y_peer[p] + off), v);
-  if (a.y_mc) {
-    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.y_mc + off), "f"(v.x), "f"(v.y),
-                 "f"(v.z), "f"(v.w)
-                 : "memory");
-  }
-}
-
-// Per-row epilogue; executed convergently by the G lanes of one group.
-template <int G, int CH, bool FULL = true>
-__device__ __forceinline__ void finish_row(const GatherArgs& a, int64_t r, const float4 (&acc)[CH], int gl,
-                                           unsigned gmask) {
+static int dispatch_width(const GatherArgs& a, cudaStream_t st, int sm_count) {
   const int V = a.d >> 2;
-  const float rs = a.row_scale ? __ldg(a.row_scale + r) : 1.f;
-  if (!FULL) {  // plain SpMM: y = row_scale * acc, nothing else requested
-#pragma unroll
-    for (int j = 0; j < CH; ++j) {
-      const int ch = gl + G * j;
-      if (ch < V) {
-        float4 v = acc[j];
-        v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
-        store_y(a, r, ch, v);
-      }
-    }
-    return;
-  }
-  const bool want_dot = a.dot_out != nullptr;
-  const bool want_ss = a.sumsq != nullptr;
-  const float4* dm = nullptr;
-  if (want_dot) {
-    const int64_t dr = a.dot_rows ? (int64_t)__ldg(a.dot_rows + r) : r;
-    dm = reinterpret_cast<const float4*>(a.dot_mat + dr * a.lddot);
-  }
-  const bool prelu = a.prelu_slope != nullptr;
-  const float slope = prelu ? __ldg(a.prelu_slope) : 0.f;
-  float ss = 0.f, dt = 0.f;
-#pragma unroll
-  for (int j = 0; j < CH; ++j) {
-    const int ch = gl + G * j;
-    if (ch < V) {
-      float4 v = acc[j];
-      v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
-      if (a.bias) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias) + ch);
-        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-      }
-      if (a.z) stg_cs_f4(reinterpret_cast<float4*>(a.z + r * a.ldy) + ch, v);
-      if (prelu) {
-        v.x = v.x >= 0.f ? v.x : slope * v.x;
-        v.y = v.y >= 0.f ? v.y : slope * v.y;
-        v.z = v.z >= 0.f ? v.z : slope * v.z;
-        v.w = v.w >= 0.f ? v.w : slope * v.w;
-      } else if (a.relu) {
-        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-      }
-      store_y(a, r, ch, v);
-      if (want_ss) ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-      if (want_dot) {
-        const float4 m = __ldg(dm + ch);
-        dt += v.x * m.x + v.y * m.y + v.z * m.z + v.w * m.w;
-      }
-    }
-  }
-  if (want_ss || want_dot) {
-#pragma unroll
-    for (int off = G / 2; off > 0; off >>= 1) {
-      ss += __shfl_xor_sync(gmask, ss, off);
-      dt += __shfl_xor_sync(gmask, dt, off);
-    }
-    if (gl == 0) {
-      if (want_ss) a.sumsq[r] = ss;
-      if (want_dot) a.dot_out[r] = dt * (a.dot_scale ? __ldg(a.dot_scale + r) : 1.f);
-    }
-  }
-}
-
-// Resolve one edge: column -> (row of x or -1 to skip, weight).
-template <bool GEN>
-__device__ __forceinline__ void resolve_edge(const GatherArgs& a, int& c, float& w) {
-  if (GEN) {
-    if (a.col_scale) w *= __ldg(a.col_scale + c);
-    if (a.xmap) c = __ldg(a.xmap + c);
-    if (w == 0.f) c = -1;  // zero-scaled columns are skipped without touching x
-  }
-}
-
-// ---------------------------------------------------------------------------
-// group-per-row kernel (no plan)
-// ---------------------------------------------------------------------------
-template <int G, int CH, bool GEN>
-__global__ void __launch_bounds__(kThreads) gather_rows_kernel(const GatherArgs a) {
-  constexpr int U = (CH == 1) ? 4 : 2;
-  const int V = a.d >> 2;
-  const int gl = threadIdx.x % G;
-  const unsigned gmask = group_mask<G>();
-  const int64_t gid = (int64_t(blockIdx.x) * kThreads + threadIdx.x) / G;
-  const int64_t ngroups = int64_t(gridDim.x) * kThreads / G;
-  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(a.x);
-  const int64_t ldx4 = a.ldx >> 2;
-  const bool has_val = a.val != nullptr;
-  for (int64_t r = gid; r < a.n_rows; r += ngroups) {
-    const int64_t e0 = __ldg(a.rowptr + r), e1 = __ldg(a.rowptr + r + 1);
-    float4 acc[CH];
-#pragma unroll
-    for (int j = 0; j < CH; ++j) acc[j] = f4_zero();
-    for (int64_t e = e0; e < e1; e += U) {
-      int c[U];
-      float w[U];
-      float4 xv[U][CH];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const bool ok = e + u < e1;
-        c[u] = ok ? __ldg(a.col + e + u) : -1;
-        w[u] = ok ? (has_val ? __ldg(a.val + e + u) : 1.f) : 0.f;
-        if (ok) resolve_edge<GEN>(a, c[u], w[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-          const int ch = gl + G * j;
-          xv[u][j] = (c[u] >= 0 && ch < V) ? ldg_f4(x4 + int64_t(c[u]) * ldx4 + ch) : f4_zero();
-        }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int j = 0; j < CH; ++j) f4_fma(acc[j], w[u], xv[u][j]);
-    }
-    finish_row<G, CH>(a, r, acc, gl, gmask);
-  }
+  if (V <= 4) return launch_g4c1(a, st, sm_count);
+  if (V <= 8) return launch_g8c1(a, st, sm_count);
+  if (V <= 16) return launch_g16c1(a, st, sm_count);
+  if (V <= 32) return launch_g32c1(a, st, sm_count);
+  if (V <= 64) return launch_g32c2(a, st, sm_count);
+  if (V <= 96) return launch_g32c3(a, st, sm_count);
+  if (V <= 128) return launch_g32c4(a, st, sm_count);
+  return launch_g32c6(a, st, sm_count);
 }
 
 // ---------------------------------------------------------------------------
@@ -219,334 +43,6 @@ __global__ void plan_kernel(const int64_t* __restrict__ rowptr, int64_t n_rows, 
   }
   tile_row[t] = (int32_t)lo;
   tile_edge[t] = diag - lo;
-}
-
-// ---------------------------------------------------------------------------
-// merge-path tiled kernel
-// ---------------------------------------------------------------------------
-template <int G, int CH>
-struct TileSmem {
-  static constexpr int NGRP = kThreads / G;
-  static constexpr int kBar = 0;                                   // uint64 mbarrier (+pad)
-  static constexpr int kCol = 16;                                  // int32[kTile + 8]
-  static constexpr int kVal = kCol + (kTile + 8) * 4;              // float[kTile + 8]
-  static constexpr int kRend = kVal + (kTile + 8) * 4;             // int32[kTile + 8]
-  static constexpr int kCi = kRend + (kTile + 8) * 4;              // int32[NGRP + 1] (+pad)
-  static constexpr int kCj = kCi + ((NGRP + 1 + 3) / 4) * 16;      // int32[NGRP + 1] (+pad)
-  static constexpr int kFlag = kCj + ((NGRP + 1 + 3) / 4) * 16;    // int32[NGRP] (+pad)
-  static constexpr int kPart = kFlag + ((NGRP + 3) / 4) * 16;      // float4[NGRP][2][G*CH]
-  static constexpr int kBytes = kPart + NGRP * 2 * G * CH * 16;
-};
-
-// MODE 0: unweighted (val == NULL), 1: per-edge val, 2: general (col_scale / xmap, optional val).
-// EPI false: plain y = row_scale * acc; true: bias / activation / z / sumsq / dot epilogue.
-template <int G, int CH, int MODE, bool EPI>
-__global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2)) gather_tiled_kernel(const GatherArgs a) {
-  using L = TileSmem<G, CH>;
-  constexpr int NGRP = L::NGRP;
-  constexpr int U = (CH == 1) ? 8 : (CH == 2 ? 4 : 2);
-  extern __shared__ __align__(16) unsigned char smem[];
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L::kBar);
-  int32_t* s_col = reinterpret_cast<int32_t*>(smem + L::kCol);
-  float* s_val = reinterpret_cast<float*>(smem + L::kVal);
-  int32_t* s_rend = reinterpret_cast<int32_t*>(smem + L::kRend);
-  int32_t* s_ci = reinterpret_cast<int32_t*>(smem + L::kCi);
-  int32_t* s_cj = reinterpret_cast<int32_t*>(smem + L::kCj);
-  int32_t* s_flag = reinterpret_cast<int32_t*>(smem + L::kFlag);
-  float4* s_part = reinterpret_cast<float4*>(smem + L::kPart);
-
-  const int tid = threadIdx.x;
-  const int64_t k = blockIdx.x;
-  const int64_t r0 = __ldg(a.tile_row + k), r1 = __ldg(a.tile_row + k + 1);
-  const int64_t e0 = __ldg(a.tile_edge + k), e1 = __ldg(a.tile_edge + k + 1);
-  const int nr = int(r1 - r0);  // rows whose end falls inside the tile
-  const int ne = int(e1 - e0);  // edges inside the tile
-  const bool has_val = a.val != nullptr;
-
-  // ---- stage the CSR slice: TMA bulk copy for col/val, plain loads for the row ends ----
-  const int64_t e0a = e0 & ~int64_t(3);  // 16-byte aligned start
-  const int lead = int(e0 - e0a);
-  const int cnt = ne + lead;
-  int nb = (cnt + 3) & ~3;
-  if (e0a + nb > a.nnz) nb = cnt & ~3;  // never read past the arrays; the ragged tail is loaded below
-  if (tid == 0) {
-    mbar_init(s_bar, 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  if (tid == 0 && nb > 0) {
-    mbar_arrive_expect_tx(s_bar, uint32_t(nb) * 4u * (has_val ? 2u : 1u));
-    tma_bulk_g2s(s_col, a.col + e0a, uint32_t(nb) * 4u, s_bar);
-    if (has_val) tma_bulk_g2s(s_val, a.val + e0a, uint32_t(nb) * 4u, s_bar);
-  }
-  for (int t = nb + tid; t < cnt; t += kThreads) {
-    s_col[t] = __ldg(a.col + e0a + t);
-    if (has_val) s_val[t] = __ldg(a.val + e0a + t);
-  }
-  for (int j = tid; j <= nr; j += kThreads) {
-    const int64_t rr = r0 + j + 1;
-    int64_t v = (rr <= a.n_rows) ? (__ldg(a.rowptr + rr) - e0) : int64_t(kBig);
-    s_rend[j] = v > kBig ? kBig : int(v);
-  }
-  // start of row r0 relative to the tile (<= 0; < 0 means the row began in an earlier tile)
-  const int rstart0 = (r0 < a.n_rows) ? int(__ldg(a.rowptr + r0) - e0) : 0;
-  __syncthreads();
-
-  // ---- second-level merge path: split (nr + ne) items evenly over the NGRP groups ----
-  const int items = nr + ne;
-  const int ipg = (items + NGRP - 1) / NGRP;
-  if (tid <= NGRP) {
-    int diag = tid * ipg;
-    if (diag > items) diag = items;
-    int lo = diag > ne ? diag - ne : 0;
-    int hi = diag < nr ? diag : nr;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (s_rend[mid] <= diag - mid - 1) lo = mid + 1;
-      else hi = mid;
-    }
-    s_ci[tid] = lo;
-    s_cj[tid] = diag - lo;
-  }
-  __syncthreads();
-  if (nb > 0) mbar_wait(s_bar, 0);
-
-  const int g = tid / G, gl = tid % G;
-  const unsigned gmask = group_mask<G>();
-  const int V = a.d >> 2;
-  float4* my_part = s_part + (g * 2) * (G * CH);
-
-  {
-    const int i1 = s_ci[g], j1 = s_cj[g], i2 = s_ci[g + 1], j2 = s_cj[g + 1];
-    int row = i1;
-    int cur_end = s_rend[row];
-    bool head_pending = ((i1 == 0) ? rstart0 : s_rend[i1 - 1]) < j1;  // first row began before this group
-    int flag = 0;
-    float4 acc[CH];
-    // Byte offset of this lane's 16-byte chunk(s) inside a row.  Lanes beyond the row width (V not a
-    // multiple of G) re-read chunk 0: their sums are never stored, and no predicate is needed in the loop.
-    const char* lane_base[CH];
-#pragma unroll
-    for (int j = 0; j < CH; ++j) {
-      acc[j] = f4_zero();
-      lane_base[j] = reinterpret_cast<const char*>(a.x) + ((gl + G * j < V) ? uint32_t(gl + G * j) * 16u : 0u);
-      asm volatile("" : "+l"(lane_base[j]));  // keep it one opaque 64-bit register pair (IMAD.WIDE addend)
-    }
-    const uint32_t row_bytes = uint32_t(a.ldx) * 4u;
-    // one IMAD.WIDE.U32 per gathered chunk: (x + lane offset) + col * row_bytes
-    auto load_chunk = [&](int c, int j) {
-      return ldg_f4(reinterpret_cast<const float4*>(lane_base[j] + uint64_t(uint32_t(c)) * row_bytes));
-    };
-    const int32_t* __restrict__ sc = s_col + lead;
-    const float* __restrict__ sv = s_val + lead;
-
-    auto flush = [&]() {
-      if (head_pending) {
-#pragma unroll
-        for (int j = 0; j < CH; ++j) my_part[gl + G * j] = acc[j];
-        flag |= 1;
-        head_pending = false;
-      } else {
-        finish_row<G, CH, EPI>(a, r0 + row, acc, gl, gmask);
-      }
-#pragma unroll
-      for (int j = 0; j < CH; ++j) acc[j] = f4_zero();
-      ++row;
-      cur_end = s_rend[row];
-    };
-    auto accumulate = [&](float w, const float4 (&v)[CH]) {
-#pragma unroll
-      for (int j = 0; j < CH; ++j) {
-        if (MODE == 0) f4_add(acc[j], v[j]);
-        else f4_fma(acc[j], w, v[j]);
-      }
-    };
-
-    int e = j1;
-    // full batches of U edges: U independent 128-bit gathers per lane in flight
-    for (; e + U <= j2; e += U) {
-      int c[U];
-      float w[U];
-      float4 xv[U][CH];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        c[u] = sc[e + u];
-        w[u] = (MODE == 0) ? 1.f : ((MODE == 1 || has_val) ? sv[e + u] : 1.f);
-        if (MODE == 2) resolve_edge<true>(a, c[u], w[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int j = 0; j < CH; ++j) xv[u][j] = (MODE < 2 || c[u] >= 0) ? load_chunk(c[u], j) : f4_zero();
-      if (e + U <= cur_end) {  // whole batch inside the current row: no boundary checks
-#pragma unroll
-        for (int u = 0; u < U; ++u) accumulate(w[u], xv[u]);
-      } else {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          while (e + u >= cur_end) flush();
-          accumulate(w[u], xv[u]);
-        }
-      }
-    }
-    if (e < j2) {  // ragged tail (< U edges)
-      int c[U];
-      float w[U];
-      float4 xv[U][CH];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const bool ok = e + u < j2;
-        c[u] = ok ? sc[e + u] : -1;
-        w[u] = ok ? ((MODE == 0) ? 1.f : ((MODE == 1 || has_val) ? sv[e + u] : 1.f)) : 0.f;
-        if (MODE == 2 && ok) resolve_edge<true>(a, c[u], w[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int j = 0; j < CH; ++j) xv[u][j] = (c[u] >= 0) ? load_chunk(c[u], j) : f4_zero();
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (e + u < j2) {
-          while (e + u >= cur_end) flush();
-          accumulate(w[u], xv[u]);
-        }
-      }
-    }
-    while (row < i2) flush();
-    // edges of row i2 consumed by this group without reaching its end -> tail partial
-    const int rs_tail = (i2 == 0) ? rstart0 : s_rend[i2 - 1];
-    if (j2 > (rs_tail > j1 ? rs_tail : j1)) {
-#pragma unroll
-      for (int j = 0; j < CH; ++j) my_part[G * CH + gl + G * j] = acc[j];
-      flag |= 2;
-    }
-    if (gl == 0) s_flag[g] = flag;
-  }
-  __syncthreads();
-
-  // ---- combine rows cut by group boundaries, in group order (group 0 does it) ----
-  if (g == 0) {
-    float4 chain[CH];
-#pragma unroll
-    for (int j = 0; j < CH; ++j) chain[j] = f4_zero();
-    float* ws_head = a.ws + (2 * k) * int64_t(a.d);
-    float* ws_tail = ws_head + a.d;
-    for (int q = 0; q < NGRP; ++q) {
-      const int f = s_flag[q];
-      const float4* part = s_part + (q * 2) * (G * CH);
-      if (f & 1) {
-#pragma unroll
-        for (int j = 0; j < CH; ++j) f4_add(chain[j], part[gl + G * j]);
-        const int row = s_ci[q];
-        if (row == 0 && rstart0 < 0) {  // began in an earlier tile: tile_fixup_kernel finishes it
-#pragma unroll
-          for (int j = 0; j < CH; ++j)
-            if (gl + G * j < V) reinterpret_cast<float4*>(ws_head)[gl + G * j] = chain[j];
-        } else {
-          finish_row<G, CH, EPI>(a, r0 + row, chain, gl, gmask);
-        }
-#pragma unroll
-        for (int j = 0; j < CH; ++j) chain[j] = f4_zero();
-      }
-      if (f & 2) {
-#pragma unroll
-        for (int j = 0; j < CH; ++j) f4_add(chain[j], part[G * CH + gl + G * j]);
-      }
-    }
-    // whatever is left belongs to row r1, which ends in a later tile (zeros if nothing)
-#pragma unroll
-    for (int j = 0; j < CH; ++j)
-      if (gl + G * j < V) reinterpret_cast<float4*>(ws_tail)[gl + G * j] = chain[j];
-  }
-}
-
-// Finish rows that were cut by tile boundaries: one lane group per tile whose first row began earlier.
-template <int G, int CH, bool EPI>
-__global__ void __launch_bounds__(kThreads) tile_fixup_kernel(const GatherArgs a) {
-  const int64_t k = (int64_t(blockIdx.x) * kThreads + threadIdx.x) / G;
-  if (k >= a.n_tiles) return;
-  const int gl = threadIdx.x % G;
-  const unsigned gmask = group_mask<G>();
-  const int V = a.d >> 2;
-  const int64_t r0 = __ldg(a.tile_row + k), r1 = __ldg(a.tile_row + k + 1);
-  if (r1 == r0 || r0 >= a.n_rows) return;                       // no row ends in this tile
-  if (__ldg(a.rowptr + r0) >= __ldg(a.tile_edge + k)) return;   // row r0 starts inside this tile
-  int64_t ks = k - 1;                                           // tiles ks..k-1 hold tail partials of row r0
-  while (ks > 0 && __ldg(a.tile_row + ks) == r0) --ks;
-  float4 acc[CH];
-#pragma unroll
-  for (int j = 0; j < CH; ++j) acc[j] = f4_zero();
-  for (int64_t q = ks; q < k; ++q) {
-    const float4* t = reinterpret_cast<const float4*>(a.ws + (2 * q + 1) * int64_t(a.d));
-#pragma unroll
-    for (int j = 0; j < CH; ++j)
-      if (gl + G * j < V) f4_add(acc[j], t[gl + G * j]);
-  }
-  const float4* h = reinterpret_cast<const float4*>(a.ws + (2 * k) * int64_t(a.d));
-#pragma unroll
-  for (int j = 0; j < CH; ++j)
-    if (gl + G * j < V) f4_add(acc[j], h[gl + G * j]);
-  finish_row<G, CH, EPI>(a, r0, acc, gl, gmask);
-}
-
-// ---------------------------------------------------------------------------
-// host dispatch
-// ---------------------------------------------------------------------------
-template <int G, int CH, int MODE, bool EPI>
-static int launch_tiled(const GatherArgs& a, cudaStream_t st) {
-  using L = TileSmem<G, CH>;
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
-    GGAD_CUDA_OK(cudaFuncSetAttribute(gather_tiled_kernel<G, CH, MODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      L::kBytes));
-    attr_done = true;
-  }
-  gather_tiled_kernel<G, CH, MODE, EPI><<<(unsigned)a.n_tiles, kThreads, L::kBytes, st>>>(a);
-  GGAD_CUDA_OK(cudaGetLastError());
-  const int64_t fix_blocks = (a.n_tiles * G + kThreads - 1) / kThreads;
-  tile_fixup_kernel<G, CH, EPI><<<(unsigned)fix_blocks, kThreads, 0, st>>>(a);
-  GGAD_CUDA_OK(cudaGetLastError());
-  count_launch(2);
-  return GGAD_OK;
-}
-
-template <int G, int CH>
-static int launch_variant(const GatherArgs& a, cudaStream_t st, int sm_count) {
-  if (a.n_rows == 0) return GGAD_OK;
-  const bool gen = a.xmap || a.col_scale;
-  if (a.tile_row) {
-    const bool epi = a.bias || a.prelu_slope || a.relu || a.z || a.sumsq || a.dot_out || (!a.y && !a.y_mc);
-    const int mode = gen ? 2 : (a.val ? 1 : 0);
-    if (epi) {
-      if (mode == 0) return launch_tiled<G, CH, 0, true>(a, st);
-      if (mode == 1) return launch_tiled<G, CH, 1, true>(a, st);
-      return launch_tiled<G, CH, 2, true>(a, st);
-    }
-    if (mode == 0) return launch_tiled<G, CH, 0, false>(a, st);
-    if (mode == 1) return launch_tiled<G, CH, 1, false>(a, st);
-    return launch_tiled<G, CH, 2, false>(a, st);
-  }
-  const int64_t gpb = kThreads / G;
-  int64_t blocks = (a.n_rows + gpb - 1) / gpb;
-  const int64_t cap = int64_t(sm_count) * 64;
-  if (blocks > cap) blocks = cap;
-  if (gen) gather_rows_kernel<G, CH, true><<<(unsigned)blocks, kThreads, 0, st>>>(a);
-  else gather_rows_kernel<G, CH, false><<<(unsigned)blocks, kThreads, 0, st>>>(a);
-  GGAD_CUDA_OK(cudaGetLastError());
-  count_launch(1);
-  return GGAD_OK;
-}
-
-static int dispatch_width(const GatherArgs& a, cudaStream_t st, int sm_count) {
-  const int V = a.d >> 2;
-  if (V <= 4) return launch_variant<4, 1>(a, st, sm_count);
-  if (V <= 8) return launch_variant<8, 1>(a, st, sm_count);
-  if (V <= 16) return launch_variant<16, 1>(a, st, sm_count);
-  if (V <= 32) return launch_variant<32, 1>(a, st, sm_count);
-  if (V <= 64) return launch_variant<32, 2>(a, st, sm_count);
-  if (V <= 96) return launch_variant<32, 3>(a, st, sm_count);
-  if (V <= 128) return launch_variant<32, 4>(a, st, sm_count);
-  return launch_variant<32, 6>(a, st, sm_count);
 }
 
 int sm_count_cached();  // api.cu
