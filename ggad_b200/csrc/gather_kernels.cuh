@@ -84,23 +84,13 @@ __device__ __forceinline__ void store_y(const GatherArgs& a, int64_t r, int ch, 
 }
 
 // Per-row epilogue; executed convergently by the G lanes of one group.
-template <int G, int CH, bool FULL = true, bool PEER = false>
-__device__ __forceinline__ void finish_row(const GatherArgs& a, int64_t r, const float4 (&acc)[CH], int gl,
-                                           unsigned gmask) {
+// Full per-row epilogue (bias / activation / z / sumsq / dot).  It is large, so kernels that use it keep the
+// number of inlined copies at two (rolled boundary path below); a non-inlined call was measured slower
+// (register spills around the call sites), 17 inlined copies 2x slower (instruction cache).
+template <int G, int CH, bool PEER>
+__device__ __forceinline__ void finish_row_full(const GatherArgs& a, int64_t r, const float4* acc, int gl, unsigned gmask) {
   const int V = a.d >> 2;
   const float rs = a.row_scale ? __ldg(a.row_scale + r) : 1.f;
-  if (!FULL) {  // plain SpMM: y = row_scale * acc, nothing else requested
-#pragma unroll
-    for (int j = 0; j < CH; ++j) {
-      const int ch = gl + G * j;
-      if (ch < V) {
-        float4 v = acc[j];
-        v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
-        store_y<PEER>(a, r, ch, v);
-      }
-    }
-    return;
-  }
   const bool want_dot = a.dot_out != nullptr;
   const bool want_ss = a.sumsq != nullptr;
   const float4* dm = nullptr;
@@ -151,6 +141,27 @@ __device__ __forceinline__ void finish_row(const GatherArgs& a, int64_t r, const
   }
 }
 
+
+template <int G, int CH, bool FULL = true, bool PEER = false>
+__device__ __forceinline__ void finish_row(const GatherArgs& a, int64_t r, const float4 (&acc)[CH], int gl,
+                                           unsigned gmask) {
+  const int V = a.d >> 2;
+  const float rs = a.row_scale ? __ldg(a.row_scale + r) : 1.f;
+  if (!FULL) {  // plain SpMM: y = row_scale * acc, nothing else requested
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const int ch = gl + G * j;
+      if (ch < V) {
+        float4 v = acc[j];
+        v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
+        store_y<PEER>(a, r, ch, v);
+      }
+    }
+    return;
+  }
+  finish_row_full<G, CH, PEER>(a, r, acc, gl, gmask);
+}
+
 // Resolve one edge: column -> (row of x or -1 to skip, weight).
 template <bool GEN>
 __device__ __forceinline__ void resolve_edge(const GatherArgs& a, int& c, float& w) {
@@ -165,7 +176,7 @@ __device__ __forceinline__ void resolve_edge(const GatherArgs& a, int& c, float&
 // group-per-row kernel (no plan)
 // ---------------------------------------------------------------------------
 template <int G, int CH, bool GEN>
-__global__ void __launch_bounds__(kThreads) gather_rows_kernel(const GatherArgs a) {
+__global__ void __launch_bounds__(kThreads) gather_rows_kernel(const __grid_constant__ GatherArgs a) {
   constexpr int U = (CH == 1) ? 4 : 2;
   const int V = a.d >> 2;
   const int gl = threadIdx.x % G;
@@ -228,7 +239,7 @@ struct TileSmem {
 // EPI false: plain y = row_scale * acc; true: bias / activation / z / sumsq / dot epilogue.
 // PEER: the epilogue also stores every finished row to the peers' replicas / the multicast address.
 template <int G, int CH, int MODE, bool EPI, bool PEER>
-__global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2)) gather_tiled_kernel(const GatherArgs a) {
+__global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2)) gather_tiled_kernel(const __grid_constant__ GatherArgs a) {
   using L = TileSmem<G, CH>;
   constexpr int NGRP = L::NGRP;
   constexpr int U = (CH == 1) ? 8 : (CH == 2 ? 4 : 2);
@@ -349,53 +360,112 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
       }
     };
 
-    int e = j1;
-    // full batches of U edges: U independent 128-bit gathers per lane in flight
-    for (; e + U <= j2; e += U) {
-      int c[U];
-      float w[U];
-      float4 xv[U][CH];
+    if constexpr (EPI) {
+      // Large epilogue: a batch that crosses row ends (and the ragged last batch) walks its rows in a rolled
+      // loop, so only three inlined copies of the epilogue exist in the kernel.
+      auto walk_rows = [&](int e, int nb, const float (&w)[U], const float4 (&xv)[U][CH]) {
+        int u0 = 0;
+        while (u0 < nb) {
+          if (e + u0 >= cur_end) {
+            flush();
+            continue;
+          }
+          const int lim = (cur_end - e < nb) ? (cur_end - e) : nb;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        c[u] = sc[e + u];
-        w[u] = (MODE == 0) ? 1.f : ((MODE == 1 || has_val) ? sv[e + u] : 1.f);
-        if (MODE == 2) resolve_edge<true>(a, c[u], w[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int j = 0; j < CH; ++j) xv[u][j] = (MODE < 2 || c[u] >= 0) ? load_chunk(c[u], j) : f4_zero();
-      if (e + U <= cur_end) {  // whole batch inside the current row: no boundary checks
-#pragma unroll
-        for (int u = 0; u < U; ++u) accumulate(w[u], xv[u]);
-      } else {
+          for (int u = 0; u < U; ++u)
+            if (u >= u0 && u < lim) accumulate(w[u], xv[u]);
+          u0 = lim;
+        }
+      };
+      int e = j1;
+      for (; e + U <= j2; e += U) {
+        int c[U];
+        float w[U];
+        float4 xv[U][CH];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          while (e + u >= cur_end) flush();
-          accumulate(w[u], xv[u]);
+          c[u] = sc[e + u];
+          w[u] = (MODE == 0) ? 1.f : ((MODE == 1 || has_val) ? sv[e + u] : 1.f);
+          if (MODE == 2) resolve_edge<true>(a, c[u], w[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int j = 0; j < CH; ++j) xv[u][j] = (MODE < 2 || c[u] >= 0) ? load_chunk(c[u], j) : f4_zero();
+        if (e + U <= cur_end) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) accumulate(w[u], xv[u]);
+        } else {
+          walk_rows(e, U, w, xv);
         }
       }
-    }
-    if (e < j2) {  // ragged tail (< U edges)
-      int c[U];
-      float w[U];
-      float4 xv[U][CH];
+      if (e < j2) {
+        const int nb = j2 - e;
+        int c[U];
+        float w[U];
+        float4 xv[U][CH];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const bool ok = e + u < j2;
-        c[u] = ok ? sc[e + u] : -1;
-        w[u] = ok ? ((MODE == 0) ? 1.f : ((MODE == 1 || has_val) ? sv[e + u] : 1.f)) : 0.f;
-        if (MODE == 2 && ok) resolve_edge<true>(a, c[u], w[u]);
+        for (int u = 0; u < U; ++u) {
+          const bool ok = u < nb;
+          c[u] = ok ? sc[e + u] : -1;
+          w[u] = ok ? ((MODE == 0) ? 1.f : ((MODE == 1 || has_val) ? sv[e + u] : 1.f)) : 0.f;
+          if (MODE == 2 && ok) resolve_edge<true>(a, c[u], w[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int j = 0; j < CH; ++j) xv[u][j] = (c[u] >= 0) ? load_chunk(c[u], j) : f4_zero();
+        walk_rows(e, nb, w, xv);
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int j = 0; j < CH; ++j) xv[u][j] = (c[u] >= 0) ? load_chunk(c[u], j) : f4_zero();
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (e + u < j2) {
-          while (e + u >= cur_end) flush();
-          accumulate(w[u], xv[u]);
+    } else {
+      int e = j1;
+      // full batches of U edges: U independent 128-bit gathers per lane in flight
+      for (; e + U <= j2; e += U) {
+        int c[U];
+        float w[U];
+        float4 xv[U][CH];
+  #pragma unroll
+        for (int u = 0; u < U; ++u) {
+          c[u] = sc[e + u];
+          w[u] = (MODE == 0) ? 1.f : ((MODE == 1 || has_val) ? sv[e + u] : 1.f);
+          if (MODE == 2) resolve_edge<true>(a, c[u], w[u]);
+        }
+  #pragma unroll
+        for (int u = 0; u < U; ++u)
+  #pragma unroll
+          for (int j = 0; j < CH; ++j) xv[u][j] = (MODE < 2 || c[u] >= 0) ? load_chunk(c[u], j) : f4_zero();
+        if (e + U <= cur_end) {  // whole batch inside the current row: no boundary checks
+  #pragma unroll
+          for (int u = 0; u < U; ++u) accumulate(w[u], xv[u]);
+        } else {
+  #pragma unroll
+          for (int u = 0; u < U; ++u) {
+            while (e + u >= cur_end) flush();
+            accumulate(w[u], xv[u]);
+          }
+        }
+      }
+      if (e < j2) {  // ragged tail (< U edges)
+        int c[U];
+        float w[U];
+        float4 xv[U][CH];
+  #pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const bool ok = e + u < j2;
+          c[u] = ok ? sc[e + u] : -1;
+          w[u] = ok ? ((MODE == 0) ? 1.f : ((MODE == 1 || has_val) ? sv[e + u] : 1.f)) : 0.f;
+          if (MODE == 2 && ok) resolve_edge<true>(a, c[u], w[u]);
+        }
+  #pragma unroll
+        for (int u = 0; u < U; ++u)
+  #pragma unroll
+          for (int j = 0; j < CH; ++j) xv[u][j] = (c[u] >= 0) ? load_chunk(c[u], j) : f4_zero();
+  #pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (e + u < j2) {
+            while (e + u >= cur_end) flush();
+            accumulate(w[u], xv[u]);
+          }
         }
       }
     }
@@ -449,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
 
 // Finish rows that were cut by tile boundaries: one lane group per tile whose first row began earlier.
 template <int G, int CH, bool EPI, bool PEER>
-__global__ void __launch_bounds__(kThreads) tile_fixup_kernel(const GatherArgs a) {
+__global__ void __launch_bounds__(kThreads) tile_fixup_kernel(const __grid_constant__ GatherArgs a) {
   const int64_t k = (int64_t(blockIdx.x) * kThreads + threadIdx.x) / G;
   if (k >= a.n_tiles) return;
   const int gl = threadIdx.x % G;

@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Time individual gather_reduce variants (CUDA events, median of N) on one workload.
+    python tools/bench_variants.py --workload C3
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import WORKLOADS  # noqa: E402
+from ggad_b200 import ops, synth  # noqa: E402
+from ggad_b200.graph import CSRGraph  # noqa: E402
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="S64")
+a = ap.parse_args()
+n, m, d = WORKLOADS[a.workload]
+g = synth.rmat_shard(n, m, seed=0)
+gw = CSRGraph(g.rowptr, g.col, torch.rand(g.nnz, device="cuda"), n, n)
+gw._plan = g.plan
+x = torch.randn(n, d, device="cuda")
+bias = torch.randn(d, device="cuda")
+slope = torch.tensor([0.25], device="cuda")
+cs = torch.rand(n, device="cuda") + 0.5
+sub = torch.randperm(n, device="cuda")[: max(1, n // 7)].to(torch.int32)
+res = {}
+res["plain unweighted (row_scale)"] = timeit(lambda: ops.gather_reduce(g, x))
+res["plain weighted"] = timeit(lambda: ops.gather_reduce(gw, x))
+res["weighted + bias + PReLU + z (GCN layer)"] = timeit(lambda: ops.gather_reduce(gw, x, bias=bias, prelu_slope=slope, want_z=True))
+res["weighted + bias + PReLU, no z"] = timeit(lambda: ops.gather_reduce(gw, x, bias=bias, prelu_slope=slope))
+res["weighted + sumsq"] = timeit(lambda: ops.gather_reduce(gw, x, want_sumsq=True))
+res["general (col_scale)"] = timeit(lambda: ops.gather_reduce(gw, x, col_scale=cs, use_graph_scales=False))
+res["general, 1/7 of columns non-zero (affinity backward)"] = timeit(
+    lambda: ops.gather_reduce(gw, x, col_scale=torch.zeros(n, device="cuda").index_fill_(0, sub.long(), 1.0), use_graph_scales=False))
+print(f"workload {a.workload}: n={n} nnz={m} d={d}")
+for k, v in res.items():
+    print(f"  {k:55s} {v:8.3f} ms   {m / v / 1e6:8.2f} G edges/s")
