@@ -43,7 +43,7 @@ def ggad_loss(emb, logits, emb_con, emb_abnormal, raw_adj, normal_label_idx, abn
     lbl = torch.cat((torch.zeros(len(normal_label_idx), device=device),
                      torch.ones(emb_con.shape[0], device=device))).unsqueeze(1).unsqueeze(0)
     loss_bce = F.binary_cross_entropy_with_logits(logits, lbl, reduction='none',
-                                                  pos_weight=torch.tensor([float(negsamp_ratio)], device=device)).mean()
+                                                  pos_weight=torch.full((1,), float(negsamp_ratio), device=device)).mean()
     # local affinity (run.py:175-191) on the consumed rows only
     e = emb[0] if emb.dim() == 3 else emb
     subset, pos_n, pos_a = _subset(normal_label_idx, abnormal_label_idx, device)

@@ -20,6 +20,23 @@ from . import ops
 from .graph import CSRGraph
 
 _graph_cache = {}
+_index_cache = {}
+
+
+def _device_index(idx, device) -> torch.Tensor:
+    """LongTensor copy of a Python index list on the device, cached on the list's identity so that the
+    forward pass issues no host->device copies (required for CUDA-graph capture)."""
+    if isinstance(idx, torch.Tensor):
+        return idx.to(device=device, dtype=torch.long)
+    key = (id(idx), len(idx), str(device))
+    hit = _index_cache.get(key)
+    if hit is None or hit[1] != (idx[0] if len(idx) else None, idx[-1] if len(idx) else None):
+        t = torch.as_tensor(list(idx), dtype=torch.long).to(device)
+        hit = (t, (idx[0] if len(idx) else None, idx[-1] if len(idx) else None))
+        if len(_index_cache) > 16:
+            _index_cache.clear()
+        _index_cache[key] = hit
+    return hit[0]
 
 
 def as_graph(adj, device) -> CSRGraph:
@@ -153,7 +170,8 @@ class Model(nn.Module):
         emb = self.gcn2(h_1, g, sparse)
         emb_con = None
         emb_combine = None
-        emb_abnormal = emb[:, sample_abnormal_idx, :]
+        s_idx = _device_index(sample_abnormal_idx, emb.device)
+        emb_abnormal = emb[:, s_idx, :]
         if noise is None:
             # drawn on the CPU generator with the reference's call, then moved (same stream of numbers)
             noise = (torch.randn(emb_abnormal.size()) * args.var + args.mean).to(emb.device)
@@ -161,10 +179,9 @@ class Model(nn.Module):
         if train_flag:
             ego = ops.spmm(g.rows(sample_abnormal_idx), emb[0])          # rows S of A_hat @ emb
             emb_con = self.act(self.fc4(ego))
-            emb_combine = torch.cat((emb[:, normal_idx, :], torch.unsqueeze(emb_con, 0)), 1)
+            emb_combine = torch.cat((emb[:, _device_index(normal_idx, emb.device), :], torch.unsqueeze(emb_con, 0)), 1)
             f_3 = self._mlp(emb_combine)
-            idx = torch.as_tensor(sample_abnormal_idx, dtype=torch.long, device=emb.device)
-            emb = emb.index_copy(1, idx, emb_con.unsqueeze(0))           # the in-place write-back of model.py:182
+            emb = emb.index_copy(1, s_idx, emb_con.unsqueeze(0))         # the in-place write-back of model.py:182
         else:
             f_3 = self._mlp(emb)
         return emb, emb_combine, f_3, emb_con, emb_abnormal

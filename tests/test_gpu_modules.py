@@ -228,3 +228,31 @@ def test_full_batch_training_auroc_parity():
     auc_gpu = roc_auc_score(labels[idx_test], s_gpu[idx_test])
     auc_ref = roc_auc_score(labels[idx_test], s_ref[idx_test])
     assert abs(auc_gpu - auc_ref) <= 0.002, (auc_gpu, auc_ref)
+
+
+def test_cuda_graph_epoch_matches_eager():
+    """The CUDA-graph replay of the full-batch epoch (forward + losses + backward + Adam) follows the eager
+    trajectory (same kernels, same order: bit-identical losses)."""
+    from ggad_b200 import graph, model, synth, train
+    n, d, h = 900, 20, 32
+    a, x, labels = synth.planted_anomaly_graph(n, 9.0, d, 0.08, seed=4)
+    _, _, _, normal, abnormal = oracle.load_mat_split(labels, "photo", 0)
+    g_hat, g_r = graph.full_batch_graphs(a, "cuda")
+    args = types.SimpleNamespace(mean=0.02, var=0.01)
+    xt = torch.from_numpy(x).cuda()
+    torch.manual_seed(0)
+    m1 = model.Model(d, h, "prelu", 1, "avg").cuda()
+    m2 = model.Model(d, h, "prelu", 1, "avg").cuda()
+    m2.load_state_dict(m1.state_dict())
+    eager = train.GraphedFullBatchStep(m1, xt, g_hat, g_r, normal, abnormal, args, use_graph=False)
+    graphed = train.GraphedFullBatchStep(m2, xt, g_hat, g_r, normal, abnormal, args, use_graph=True)
+    for k, v in m1.state_dict().items():
+        assert torch.equal(v, m2.state_dict()[k]), f"warm-up changed {k}"
+    gen = torch.Generator().manual_seed(3)
+    for ep in range(6):
+        noise = torch.randn(1, len(abnormal), h, generator=gen) * 0.01 + 0.02
+        le = [float(t) for t in eager.step(noise)]
+        lg = [float(t) for t in graphed.step(noise)]
+        assert_close(torch.tensor(lg), torch.tensor(le), rtol=1e-5, atol=1e-6, what=f"epoch {ep}")
+    for k, v in m1.state_dict().items():
+        assert_close(m2.state_dict()[k], v, rtol=1e-4, atol=1e-6, what=k)
