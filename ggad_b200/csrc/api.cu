@@ -50,6 +50,12 @@ int normalize_backward_impl(const float*, int64_t, const float*, float*, int64_t
 int rmat_keys_impl(uint64_t*, int64_t, int64_t, int32_t, int32_t, uint64_t, float, float, float, int64_t, int64_t, int64_t*,
                    cudaStream_t);
 
+int block_rowptr_impl(const int64_t*, const int32_t*, int64_t, const int32_t*, int64_t, int, int64_t*, int64_t*, cudaStream_t);
+int block_fill_impl(const int64_t*, const int32_t*, int64_t, const int32_t*, int64_t, int, const int64_t*, int32_t*,
+                    cudaStream_t);
+int unique_sorted_impl(const int32_t*, int64_t, int64_t, int32_t*, int64_t*, cudaStream_t);
+int block_remap_impl(const int32_t*, int64_t, const int32_t*, int64_t, int32_t*, int32_t*, cudaStream_t);
+
 // deterministic single-block sum of n floats into a double
 __global__ void sum_to_double_kernel(const float* __restrict__ v, int64_t n, double scale, double* __restrict__ out) {
   __shared__ double sh[1024];
@@ -167,6 +173,30 @@ GGAD_API int ggad_csr_extract_rows(const int64_t* rowptr, const int32_t* col, co
 
 GGAD_API int ggad_col_histogram(const int32_t* col, int64_t nnz, int32_t* counts, int64_t n_cols, ggad_stream_t stream) {
   return col_histogram_impl(col, nnz, counts, n_cols, (cudaStream_t)stream);
+}
+
+GGAD_API int ggad_block_rowptr(const int64_t* adj_rowptr, const int32_t* adj_col, int64_t n_nodes, const int32_t* nodes,
+                               int64_t n_batch, int32_t add_self, int64_t* block_rowptr, int64_t* nnz_host,
+                               ggad_stream_t stream) {
+  return block_rowptr_impl(adj_rowptr, adj_col, n_nodes, nodes, n_batch, add_self, block_rowptr, nnz_host,
+                           (cudaStream_t)stream);
+}
+
+GGAD_API int ggad_block_fill(const int64_t* adj_rowptr, const int32_t* adj_col, int64_t n_nodes, const int32_t* nodes,
+                             int64_t n_batch, int32_t add_self, const int64_t* block_rowptr, int32_t* block_col,
+                             ggad_stream_t stream) {
+  return block_fill_impl(adj_rowptr, adj_col, n_nodes, nodes, n_batch, add_self, block_rowptr, block_col,
+                         (cudaStream_t)stream);
+}
+
+GGAD_API int ggad_unique_sorted(const int32_t* keys, int64_t n, int64_t key_bound, int32_t* uniq, int64_t* n_unique_host,
+                                ggad_stream_t stream) {
+  return unique_sorted_impl(keys, n, key_bound, uniq, n_unique_host, (cudaStream_t)stream);
+}
+
+GGAD_API int ggad_block_remap(const int32_t* cols, int64_t nnz, const int32_t* uniq, int64_t n_unique, int32_t* local,
+                              int32_t* cdeg, ggad_stream_t stream) {
+  return block_remap_impl(cols, nnz, uniq, n_unique, local, cdeg, (cudaStream_t)stream);
 }
 
 GGAD_API int ggad_rmat_keys(uint64_t* keys, int64_t n_edges, int64_t n_local, int32_t n_shards, int32_t shard, uint64_t seed, float a,

@@ -71,6 +71,71 @@ __global__ void col_hist_kernel(const int32_t* __restrict__ col, int64_t nnz, in
   for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < nnz; e += stride) atomicAdd(counts + col[e], 1);
 }
 
+// ---- mini-batch frontier (src/graphsage.py:305-311,335-341 as array ops on the device) ----
+// degree of block row i = |N(nodes[i])| (+1 for the node itself when add_self and it is not already a neighbor)
+__global__ void block_degree_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n_nodes,
+                                    const int32_t* __restrict__ nodes, int64_t n_batch, int add_self,
+                                    int64_t* __restrict__ deg) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i > n_batch) return;
+  if (i == n_batch) {
+    deg[i] = 0;  // scan sentinel
+    return;
+  }
+  const int64_t v = nodes[i];
+  int64_t d = 0;
+  bool has_self = false;
+  if (v >= 0 && v < n_nodes) {
+    const int64_t s = rowptr[v], e = rowptr[v + 1];
+    d = e - s;
+    if (add_self) {  // neighbor lists are sorted: binary search for v
+      int64_t lo = s, hi = e;
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (col[mid] < v) lo = mid + 1;
+        else hi = mid;
+      }
+      has_self = lo < e && col[lo] == v;
+    }
+  }
+  deg[i] = d + ((add_self && !has_self) ? 1 : 0);
+}
+
+// one warp per block row: copy the neighbor slice, append the node itself if it was not a neighbor
+__global__ void block_fill_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n_nodes,
+                                  const int32_t* __restrict__ nodes, int64_t n_batch, int add_self,
+                                  const int64_t* __restrict__ block_rowptr, int32_t* __restrict__ out) {
+  const int64_t w = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n_batch) return;
+  const int64_t v = nodes[w];
+  const int64_t o = block_rowptr[w], total = block_rowptr[w + 1] - o;
+  int64_t s = 0, n = 0;
+  if (v >= 0 && v < n_nodes) {
+    s = rowptr[v];
+    n = rowptr[v + 1] - s;
+  }
+  for (int64_t t = lane; t < n; t += 32) out[o + t] = col[s + t];
+  if (add_self && total > n && lane == 0) out[o + n] = int32_t(v);
+}
+
+// block column (global id) -> position in the sorted frontier, plus the exact batch-local column degree
+__global__ void block_remap_kernel(const int32_t* __restrict__ cols, int64_t nnz, const int32_t* __restrict__ uniq,
+                                   int64_t n_unique, int32_t* __restrict__ local, int32_t* __restrict__ cdeg) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+    const int32_t c = cols[e];
+    int64_t lo = 0, hi = n_unique;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (uniq[mid] < c) lo = mid + 1;
+      else hi = mid;
+    }
+    local[e] = int32_t(lo);
+    atomicAdd(cdeg + lo, 1);
+  }
+}
+
 // ---- dense per-row helpers of the affinity path (warp per row) ----
 __global__ void row_inv_norm_kernel(const float* __restrict__ x, int64_t ldx, int64_t n_rows, int d,
                                     float* __restrict__ inv_norm, float* __restrict__ sumsq) {
@@ -301,6 +366,87 @@ int col_histogram_impl(const int32_t* col, int64_t nnz, int32_t* counts, int64_t
   unsigned blocks = blocks_for(nnz);
   if (blocks > 148u * 32u) blocks = 148u * 32u;
   col_hist_kernel<<<blocks, 256, 0, st>>>(col, nnz, counts);
+  GGAD_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return GGAD_OK;
+}
+
+
+int block_rowptr_impl(const int64_t* rowptr, const int32_t* col, int64_t n_nodes, const int32_t* nodes, int64_t n_batch,
+                      int add_self, int64_t* block_rowptr, int64_t* nnz_host, cudaStream_t st) {
+  GGAD_REQUIRE(rowptr && (nodes || n_batch == 0) && block_rowptr && nnz_host && n_batch >= 0 && n_nodes >= 0,
+               GGAD_ERR_INVALID, "block_rowptr: bad arguments");
+  int64_t* deg = nullptr;
+  GGAD_CUDA_OK(cudaMallocAsync(&deg, size_t(n_batch + 1) * 8, st));
+  block_degree_kernel<<<blocks_for(n_batch + 1), 256, 0, st>>>(rowptr, col, n_nodes, nodes, n_batch, add_self, deg);
+  GGAD_CUDA_OK(cudaGetLastError());
+  size_t tmp_bytes = 0;
+  GGAD_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, deg, block_rowptr, n_batch + 1, st));
+  void* tmp = nullptr;
+  GGAD_CUDA_OK(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 8, st));
+  GGAD_CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, deg, block_rowptr, n_batch + 1, st));
+  count_launch(2);
+  GGAD_CUDA_OK(cudaMemcpyAsync(nnz_host, block_rowptr + n_batch, 8, cudaMemcpyDeviceToHost, st));
+  GGAD_CUDA_OK(cudaFreeAsync(tmp, st));
+  GGAD_CUDA_OK(cudaFreeAsync(deg, st));
+  GGAD_CUDA_OK(cudaStreamSynchronize(st));
+  return GGAD_OK;
+}
+
+int block_fill_impl(const int64_t* rowptr, const int32_t* col, int64_t n_nodes, const int32_t* nodes, int64_t n_batch,
+                    int add_self, const int64_t* block_rowptr, int32_t* block_col, cudaStream_t st) {
+  GGAD_REQUIRE(rowptr && (nodes || n_batch == 0) && block_rowptr && n_batch >= 0, GGAD_ERR_INVALID, "block_fill: bad arguments");
+  if (n_batch == 0) return GGAD_OK;
+  block_fill_kernel<<<blocks_for(n_batch * 32), 256, 0, st>>>(rowptr, col, n_nodes, nodes, n_batch, add_self, block_rowptr,
+                                                              block_col);
+  GGAD_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return GGAD_OK;
+}
+
+int unique_sorted_impl(const int32_t* keys, int64_t n, int64_t key_bound, int32_t* uniq, int64_t* n_unique_host,
+                       cudaStream_t st) {
+  GGAD_REQUIRE(n >= 0 && n_unique_host && (n == 0 || (keys && uniq)), GGAD_ERR_INVALID, "unique_sorted: bad arguments");
+  if (n == 0) {
+    *n_unique_host = 0;
+    return GGAD_OK;
+  }
+  uint32_t *k0 = nullptr, *k1 = nullptr;
+  int64_t* d_count = nullptr;
+  GGAD_CUDA_OK(cudaMallocAsync(&k0, size_t(n) * 4, st));
+  GGAD_CUDA_OK(cudaMallocAsync(&k1, size_t(n) * 4, st));
+  GGAD_CUDA_OK(cudaMallocAsync(&d_count, 8, st));
+  GGAD_CUDA_OK(cudaMemcpyAsync(k0, keys, size_t(n) * 4, cudaMemcpyDeviceToDevice, st));
+  cub::DoubleBuffer<uint32_t> db(k0, k1);
+  size_t sort_bytes = 0, sel_bytes = 0;
+  const int end_bit = bits_for(key_bound > 1 ? key_bound : 2);
+  GGAD_CUDA_OK(cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, db, n, 0, end_bit, st));
+  GGAD_CUDA_OK(cub::DeviceSelect::Unique(nullptr, sel_bytes, k0, reinterpret_cast<uint32_t*>(uniq), d_count, n, st));
+  void* tmp = nullptr;
+  const size_t tmp_bytes = sort_bytes > sel_bytes ? sort_bytes : sel_bytes;
+  GGAD_CUDA_OK(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 8, st));
+  size_t b = sort_bytes;
+  GGAD_CUDA_OK(cub::DeviceRadixSort::SortKeys(tmp, b, db, n, 0, end_bit, st));
+  b = sel_bytes;
+  GGAD_CUDA_OK(cub::DeviceSelect::Unique(tmp, b, db.Current(), reinterpret_cast<uint32_t*>(uniq), d_count, n, st));
+  GGAD_CUDA_OK(cudaMemcpyAsync(n_unique_host, d_count, 8, cudaMemcpyDeviceToHost, st));
+  GGAD_CUDA_OK(cudaFreeAsync(tmp, st));
+  GGAD_CUDA_OK(cudaFreeAsync(k0, st));
+  GGAD_CUDA_OK(cudaFreeAsync(k1, st));
+  GGAD_CUDA_OK(cudaFreeAsync(d_count, st));
+  GGAD_CUDA_OK(cudaStreamSynchronize(st));
+  return GGAD_OK;
+}
+
+int block_remap_impl(const int32_t* cols, int64_t nnz, const int32_t* uniq, int64_t n_unique, int32_t* local,
+                     int32_t* cdeg, cudaStream_t st) {
+  GGAD_REQUIRE(nnz >= 0 && n_unique >= 0 && cdeg && (nnz == 0 || (cols && uniq && local)), GGAD_ERR_INVALID,
+               "block_remap: bad arguments");
+  GGAD_CUDA_OK(cudaMemsetAsync(cdeg, 0, size_t(n_unique) * 4, st));
+  if (nnz == 0) return GGAD_OK;
+  unsigned blocks = blocks_for(nnz);
+  if (blocks > 148u * 16u) blocks = 148u * 16u;
+  block_remap_kernel<<<blocks, 256, 0, st>>>(cols, nnz, uniq, n_unique, local, cdeg);
   GGAD_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return GGAD_OK;

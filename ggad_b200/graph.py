@@ -246,6 +246,15 @@ class AdjListCSR:
         self.rowptr, self.col, self.n = rowptr, col, n_nodes
         self.n_keys = len(adj_lists)
 
+    def device(self, device) -> "DeviceAdjacency":
+        """Device copy of the adjacency CSR (uploaded once per device)."""
+        key = str(device)
+        cache = self.__dict__.setdefault("_dev", {})
+        if key not in cache:
+            cache[key] = DeviceAdjacency(torch.from_numpy(self.rowptr).to(device),
+                                         torch.from_numpy(self.col.astype(np.int32)).to(device), self.n)
+        return cache[key]
+
     @classmethod
     def get(cls, adj_lists) -> "AdjListCSR":
         key = id(adj_lists)
@@ -281,6 +290,44 @@ class AdjListCSR:
             out_ptr = np.zeros(len(nodes) + 1, dtype=np.int64)
             np.cumsum(np.bincount(rows, minlength=len(nodes)), out=out_ptr[1:])
         return out_ptr, cols
+
+
+class DeviceAdjacency:
+    """Adjacency lists as a device CSR (rowptr int64, col int32 with sorted neighbor ids) -- the input of the
+    device-side frontier construction (ggad_block_* entry points)."""
+
+    def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, n: int):
+        _lib.require_cuda(rowptr, "rowptr")
+        assert rowptr.dtype == torch.int64 and col.dtype == torch.int32
+        self.rowptr, self.col, self.n, self.device = rowptr.contiguous(), col.contiguous(), int(n), rowptr.device
+
+    def block(self, nodes: torch.Tensor, add_self: bool):
+        """One aggregation hop for ``nodes`` (int32 device tensor): the union frontier and the block CSR with
+        exact integer degrees, all on the device.  Two host round trips (block nnz and |frontier|).
+        Returns dict(frontier, rowptr, col, cdeg, n_rows, n_cols) of device tensors / ints."""
+        import ctypes as C
+        dev = self.device
+        nodes = nodes.to(device=dev, dtype=torch.int32).contiguous()
+        nb = int(nodes.numel())
+        block_rowptr = torch.empty(nb + 1, dtype=torch.int64, device=dev)
+        nnz = C.c_int64(0)
+        h = lib()
+        with torch.cuda.device(dev):
+            st = stream_ptr(dev)
+            check(h.ggad_block_rowptr(ptr(self.rowptr), ptr(self.col), self.n, ptr(nodes), nb, int(add_self),
+                                      ptr(block_rowptr), C.addressof(nnz), st))
+            m = int(nnz.value)
+            cols = torch.empty(max(m, 1), dtype=torch.int32, device=dev)
+            check(h.ggad_block_fill(ptr(self.rowptr), ptr(self.col), self.n, ptr(nodes), nb, int(add_self),
+                                    ptr(block_rowptr), ptr(cols), st))
+            uniq = torch.empty(max(m, 1), dtype=torch.int32, device=dev)
+            nu = C.c_int64(0)
+            check(h.ggad_unique_sorted(ptr(cols), m, 1 << 31, ptr(uniq), C.addressof(nu), st))
+            k = int(nu.value)
+            local = torch.empty(max(m, 1), dtype=torch.int32, device=dev)
+            cdeg = torch.empty(max(k, 1), dtype=torch.int32, device=dev)
+            check(h.ggad_block_remap(ptr(cols), m, ptr(uniq), k, ptr(local), ptr(cdeg), st))
+        return dict(frontier=uniq[:k], rowptr=block_rowptr, col=local[:m], cdeg=cdeg[:k], n_rows=nb, n_cols=k)
 
 
 def batch_block(adj: AdjListCSR, nodes: Sequence[int], add_self: bool):

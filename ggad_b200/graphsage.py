@@ -59,20 +59,44 @@ def _feature_table(features) -> Optional[torch.Tensor]:
 
 
 class _Block:
-    """One aggregation hop of a mini-batch: frontier ids + block CSR on the device."""
+    """One aggregation hop of a mini-batch: frontier ids + block CSR on the device, exact integer degrees.
+    Built either from host arrays (explicit neighbor sets) or entirely on the device (DeviceAdjacency.block)."""
 
-    def __init__(self, rowptr: np.ndarray, cols_global: np.ndarray, device):
+    def __init__(self, n_rows, n_cols, rowptr_d, col_d, frontier_d, cdeg_i, device):
+        self.n_rows, self.n_cols, self.device = int(n_rows), int(n_cols), device
+        self.rowptr_d, self.col_d, self.frontier_d = rowptr_d, col_d, frontier_d
+        self.rdeg_i = rowptr_d[1:] - rowptr_d[:-1]                 # int64, exact
+        self.cdeg_i = cdeg_i                                       # int32, exact
+        self.rdeg_d = self.rdeg_i.to(torch.float32)
+        self.cdeg_d = cdeg_i.to(torch.float32)
+
+    @classmethod
+    def from_host(cls, rowptr: np.ndarray, cols_global: np.ndarray, device) -> "_Block":
         frontier, col_local = np.unique(cols_global, return_inverse=True)
-        self.frontier = frontier                                   # sorted global ids (host)
-        self.rdeg = np.diff(rowptr)                                # exact ints
-        self.cdeg = np.bincount(col_local, minlength=len(frontier)).astype(np.int64)
-        self.n_rows, self.n_cols = len(rowptr) - 1, len(frontier)
-        self.rowptr_d = torch.from_numpy(rowptr.astype(np.int64)).to(device, non_blocking=True)
-        self.col_d = torch.from_numpy(col_local.astype(np.int32)).to(device, non_blocking=True)
-        self.frontier_d = torch.from_numpy(frontier.astype(np.int32)).to(device, non_blocking=True)
-        self.rdeg_d = torch.from_numpy(self.rdeg.astype(np.float32)).to(device, non_blocking=True)
-        self.cdeg_d = torch.from_numpy(self.cdeg.astype(np.float32)).to(device, non_blocking=True)
-        self.device = device
+        cdeg = np.bincount(col_local, minlength=len(frontier)).astype(np.int32)
+        return cls(len(rowptr) - 1, len(frontier),
+                   torch.from_numpy(rowptr.astype(np.int64)).to(device, non_blocking=True),
+                   torch.from_numpy(col_local.astype(np.int32)).to(device, non_blocking=True),
+                   torch.from_numpy(frontier.astype(np.int32)).to(device, non_blocking=True),
+                   torch.from_numpy(cdeg).to(device, non_blocking=True), device)
+
+    @classmethod
+    def from_device(cls, adj_dev, nodes_d: torch.Tensor, add_self: bool) -> "_Block":
+        b = adj_dev.block(nodes_d, add_self)
+        return cls(b["n_rows"], b["n_cols"], b["rowptr"], b["col"], b["frontier"], b["cdeg"], adj_dev.device)
+
+    # host views (tests / API parity); the training path never touches them
+    @property
+    def frontier(self) -> np.ndarray:
+        return self.frontier_d.cpu().numpy().astype(np.int64)
+
+    @property
+    def rdeg(self) -> np.ndarray:
+        return self.rdeg_i.cpu().numpy()
+
+    @property
+    def cdeg(self) -> np.ndarray:
+        return self.cdeg_i.cpu().numpy().astype(np.int64)
 
     def graph(self, mode: str) -> CSRGraph:
         """'sym': 1/sqrt(rdeg) * 1/sqrt(cdeg) (src/graphsage.py:314-318); 'mean': 1/rdeg (:316-317, :92-93).
@@ -111,12 +135,18 @@ class _LazyNeighs(list):
 
 
 def _block_for(nodes, to_neighs, adj_lists, add_self, device) -> _Block:
-    nodes = [int(n) for n in nodes]
+    """Block of one hop.  Explicit neighbor sets (a caller-supplied ``to_neighs`` list) are honoured on the
+    host; otherwise the frontier is built on the device from the cached adjacency CSR."""
     if isinstance(to_neighs, _LazyNeighs) or to_neighs is None:
-        rowptr, cols = AdjListCSR.get(adj_lists).neighbors(np.asarray(nodes, dtype=np.int64), add_self)
-    else:
-        rowptr, cols = _rows_from_sets(to_neighs, nodes, add_self)
-    return _Block(rowptr, cols, device)
+        adj_dev = adj_lists if hasattr(adj_lists, "block") else AdjListCSR.get(adj_lists).device(device)
+        if isinstance(nodes, torch.Tensor):
+            nodes_d = nodes
+        else:
+            nodes_d = torch.as_tensor([int(n) for n in nodes], dtype=torch.int32).to(device, non_blocking=True)
+        return _Block.from_device(adj_dev, nodes_d, add_self)
+    nodes = [int(n) for n in nodes]
+    rowptr, cols = _rows_from_sets(to_neighs, nodes, add_self)
+    return _Block.from_host(rowptr, cols, device)
 
 
 def _aggregate(block: _Block, mode: str, features, device) -> torch.Tensor:
@@ -126,7 +156,7 @@ def _aggregate(block: _Block, mode: str, features, device) -> torch.Tensor:
     if table is not None:
         d = features.weight.shape[1]
         return ops.spmm(g, table, xmap=block.frontier_d)[:, :d]
-    embed = features(torch.from_numpy(block.frontier).long().to(device))      # callable (stacked encoders)
+    embed = features(block.frontier_d.long())                                   # callable (stacked encoders)
     return ops.spmm(g, embed)
 
 
@@ -145,7 +175,7 @@ class BlockMask:
     def to_dense(self) -> torch.Tensor:
         b = self.block
         m = torch.zeros(self.shape, device=b.device)
-        rows = torch.repeat_interleave(torch.arange(b.n_rows, device=b.device), torch.from_numpy(b.rdeg).to(b.device))
+        rows = torch.repeat_interleave(torch.arange(b.n_rows, device=b.device), b.rdeg_i)
         m[rows, b.col_d.long()] = (1.0 / b.rdeg_d)[rows]
         return m
 
@@ -241,7 +271,7 @@ class GCNAggregator(nn.Module):
         to_feats = _aggregate(hop1, "sym", self.features, device)
         to_feats_neigh = None
         if train_flag == True:
-            hop2 = _block_for(hop1.frontier.tolist(), None, adj_list, False, device)   # no self union (:335)
+            hop2 = _block_for(hop1.frontier_d, None, adj_list, False, device)        # no self union (:335)
             to_feats_neigh = _aggregate(hop2, "sym", self.features, device)
             self.last_blocks = (hop1, hop2)
         else:

@@ -127,3 +127,28 @@ def power_law_adj_lists(n: int, avg_deg: float, seed: int = 0, alpha: float = 2.
             adj[v].add(t)
             adj[t].add(v)
     return adj
+
+
+def rmat_adjacency(n: int, n_edges: int, seed: int = 0, device="cuda"):
+    """Symmetric, duplicate-free, self-loop-free R-MAT adjacency as a DeviceAdjacency (sorted neighbor lists) --
+    the DGraph-shaped input of program B without going through a Python dict of sets.  ``n_edges`` directed
+    candidates are generated; the stored entry count (both directions, after de-duplication) is returned by
+    ``adj.col.numel()``."""
+    from .graph import DeviceAdjacency
+    device = torch.device(device)
+    keys = torch.empty(n_edges, dtype=torch.int64, device=device)
+    a, b, c = RMAT_ABC
+    with torch.cuda.device(device):
+        check(lib().ggad_rmat_keys(ptr(keys), n_edges, n, 1, 0, seed, a, b, c, 0, 0, None, stream_ptr(device)))
+    dst, src = keys >> 32, keys & 0xffffffff
+    keep = dst != src
+    dst, src = dst[keep], src[keep]
+    both = torch.cat([(dst << 32) | src, (src << 32) | dst])
+    del keys, dst, src, keep
+    both = torch.unique(both)                        # sorted + de-duplicated
+    m = int(both.numel())
+    rowptr = torch.empty(n + 1, dtype=torch.int64, device=device)
+    col = torch.empty(m, dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        check(lib().ggad_coo_keys_to_csr(ptr(both), m, n, ptr(rowptr), ptr(col), stream_ptr(device)))
+    return DeviceAdjacency(rowptr, col, n)

@@ -152,6 +152,27 @@ GGAD_API int ggad_csr_extract_rows(const int64_t* rowptr, const int32_t* col, co
 /* integer in-degree histogram of col[] (int32 counts, exact) */
 GGAD_API int ggad_col_histogram(const int32_t* col, int64_t nnz, int32_t* counts, int64_t n_cols, ggad_stream_t stream);
 
+/* ---- K7: mini-batch frontier on the device --------------------------------------------------
+ * Replaces the Python set unions of GCNAggregator / MeanAggregator (src/graphsage.py:305-311,335-341,
+ * 82-88).  adj_rowptr/adj_col is the device CSR of the adjacency lists (neighbor ids sorted, as built
+ * from the un-pickled dict of src/utils.py:27-28).  One aggregation hop is
+ *   ggad_block_rowptr  -> exact integer row degrees |N(v)| (+ the node itself if add_self and absent),
+ *                         exclusive scan into block_rowptr[n_batch+1]; *nnz_host = total (synchronises)
+ *   ggad_block_fill    -> block columns as GLOBAL ids
+ *   ggad_unique_sorted -> the frontier: sorted unique ids; *n_unique_host = |U| (synchronises)
+ *   ggad_block_remap   -> block columns as positions in the frontier + exact batch-local column degrees
+ * All outputs are integers and bit-exact with the CPU restatement. */
+GGAD_API int ggad_block_rowptr(const int64_t* adj_rowptr, const int32_t* adj_col, int64_t n_nodes, const int32_t* nodes,
+                               int64_t n_batch, int32_t add_self, int64_t* block_rowptr, int64_t* nnz_host,
+                               ggad_stream_t stream);
+GGAD_API int ggad_block_fill(const int64_t* adj_rowptr, const int32_t* adj_col, int64_t n_nodes, const int32_t* nodes,
+                             int64_t n_batch, int32_t add_self, const int64_t* block_rowptr, int32_t* block_col,
+                             ggad_stream_t stream);
+GGAD_API int ggad_unique_sorted(const int32_t* keys, int64_t n, int64_t key_bound, int32_t* uniq /*[n]*/,
+                                int64_t* n_unique_host, ggad_stream_t stream);
+GGAD_API int ggad_block_remap(const int32_t* cols, int64_t nnz, const int32_t* uniq, int64_t n_unique,
+                              int32_t* local /*[nnz]*/, int32_t* cdeg /*[n_unique]*/, ggad_stream_t stream);
+
 /* ---- synthetic graphs (C5 / S64 generator) -------------------------
  * R-MAT (a,b,c,d) edges for destination shard `shard` of `n_shards` (power of two), each shard
  * owning n_local nodes; emits keys (dst_global << 32 | src_global), dst in the shard's range,

@@ -254,6 +254,49 @@ def test_spmm_autograd_large_powerlaw():
     assert torch.equal(y.detach(), y2)
 
 
+def test_device_frontier_bit_exact_vs_host():
+    """ggad_block_* (device frontier: degrees, union, remap, batch-local column degrees) == host numpy path,
+    including duplicate batch ids, isolated nodes and ids outside the adjacency."""
+    _, _, graph, _, synth = _mods()
+    adj = synth.power_law_adj_lists(3000, 7.0, seed=5)
+    adj[17] = set()                      # isolated
+    for v in list(adj):
+        adj[v].discard(17)
+    acsr = graph.AdjListCSR(adj)
+    dev = acsr.device("cuda")
+    rng = np.random.default_rng(0)
+    nodes = rng.integers(0, 3000, 200).tolist() + [17, 17, 5, 5, 2999, 3005]
+    for add_self in (True, False):
+        ref = graph.batch_block(acsr, nodes, add_self)
+        got = dev.block(torch.tensor(nodes, dtype=torch.int32), add_self)
+        assert np.array_equal(got["frontier"].cpu().numpy(), ref["frontier"].astype(np.int32))
+        assert np.array_equal(got["rowptr"].cpu().numpy(), ref["rowptr"])
+        assert np.array_equal(got["cdeg"].cpu().numpy(), ref["cdeg"].astype(np.int32))
+        # same column SETS per row (the device appends the self id instead of inserting it in order)
+        rp, a, b = ref["rowptr"], got["col"].cpu().numpy(), ref["col"]
+        for i in range(len(nodes)):
+            assert np.array_equal(np.sort(a[rp[i]:rp[i + 1]]), np.sort(b[rp[i]:rp[i + 1]]))
+    # hop 2 from the device frontier
+    hop1 = dev.block(torch.tensor(nodes, dtype=torch.int32), True)
+    ref1 = graph.batch_block(acsr, nodes, True)
+    hop2 = dev.block(hop1["frontier"], False)
+    ref2 = graph.batch_block(acsr, ref1["frontier"], False)
+    assert np.array_equal(hop2["frontier"].cpu().numpy(), ref2["frontier"].astype(np.int32))
+    assert np.array_equal(hop2["cdeg"].cpu().numpy(), ref2["cdeg"].astype(np.int32))
+    # empty batch
+    e = dev.block(torch.zeros(0, dtype=torch.int32), True)
+    assert e["n_rows"] == 0 and e["n_cols"] == 0
+
+
+def test_rmat_adjacency_is_a_simple_graph():
+    _, _, graph, _, synth = _mods()
+    adj = synth.rmat_adjacency(20000, 200000, seed=1)
+    rp, col = adj.rowptr.cpu().numpy(), adj.col.cpu().numpy()
+    m = sp.csr_matrix((np.ones(len(col)), col, rp), shape=(20000, 20000))
+    assert (abs(m - m.T)).nnz == 0 and m.diagonal().sum() == 0 and m.data.max() == 1
+    assert all(np.all(np.diff(col[rp[i]:rp[i + 1]]) > 0) for i in range(0, 20000, 97))
+
+
 def test_rmat_generator_and_shards():
     _, _, graph, ops, synth = _mods()
     n_local, n_edges, shards = 5000, 60000, 4
