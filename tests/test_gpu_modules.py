@@ -256,3 +256,14 @@ def test_cuda_graph_epoch_matches_eager():
         assert_close(torch.tensor(lg), torch.tensor(le), rtol=1e-5, atol=1e-6, what=f"epoch {ep}")
     for k, v in m1.state_dict().items():
         assert_close(m2.state_dict()[k], v, rtol=1e-4, atol=1e-6, what=k)
+
+
+def test_on_device_auroc_matches_sklearn():
+    from sklearn.metrics import average_precision_score, roc_auc_score
+    from ggad_b200 import metrics
+    rng = np.random.default_rng(1)
+    y = (rng.random(200000) < 0.05).astype(np.int64)
+    s = np.round(rng.standard_normal(200000) + 0.7 * y, 2).astype(np.float32)
+    auc = float(metrics.roc_auc(torch.from_numpy(s).cuda(), torch.from_numpy(y).cuda()))
+    ap = float(metrics.average_precision(torch.from_numpy(s).cuda(), torch.from_numpy(y).cuda()))
+    assert abs(auc - roc_auc_score(y, s)) < 1e-9 and abs(ap - average_precision_score(y, s)) < 1e-9

@@ -80,3 +80,21 @@ def test_planted_graph_and_power_law_generators():
     adj = synth.power_law_adj_lists(500, 6.0, seed=2)
     assert all(v in adj[u] for u in adj for v in adj[u]) and all(u not in adj[u] for u in adj)
     assert max(len(s) for s in adj.values()) > 8 * np.mean([len(s) for s in adj.values()])
+
+
+def test_device_metrics_match_sklearn_on_cpu_tensors():
+    """metrics.py is plain tensor code (sort + prefix sums): checked here on CPU tensors against sklearn,
+    including heavy ties; the GPU suite re-runs it on CUDA tensors."""
+    from sklearn.metrics import average_precision_score, roc_auc_score
+    from ggad_b200 import metrics
+    rng = np.random.default_rng(0)
+    for n, ties in ((500, False), (2000, True), (50, True)):
+        y = (rng.random(n) < 0.15).astype(np.int64)
+        y[:2] = [0, 1]
+        s = rng.standard_normal(n) + y * 0.8
+        if ties:
+            s = np.round(s, 1)
+        auc = float(metrics.roc_auc(torch.from_numpy(s), torch.from_numpy(y)))
+        ap = float(metrics.average_precision(torch.from_numpy(s), torch.from_numpy(y)))
+        assert abs(auc - roc_auc_score(y, s)) < 1e-12
+        assert abs(ap - average_precision_score(y, s)) < 1e-12
