@@ -221,13 +221,13 @@ __global__ void __launch_bounds__(kThreads) gather_rows_kernel(const __grid_cons
 // ---------------------------------------------------------------------------
 // merge-path tiled kernel
 // ---------------------------------------------------------------------------
-template <int G, int CH>
+template <int G, int CH, bool HASVAL = true>
 struct TileSmem {
   static constexpr int NGRP = kThreads / G;
   static constexpr int kBar = 0;                                   // uint64 mbarrier (+pad)
   static constexpr int kCol = 16;                                  // int32[kTile + 8]
-  static constexpr int kVal = kCol + (kTile + 8) * 4;              // float[kTile + 8]
-  static constexpr int kRend = kVal + (kTile + 8) * 4;             // int32[kTile + 8]
+  static constexpr int kVal = kCol + (kTile + 8) * 4;              // float[kTile + 8] (absent when unweighted)
+  static constexpr int kRend = kVal + (HASVAL ? (kTile + 8) * 4 : 0);  // int32[kTile + 8]
   static constexpr int kCi = kRend + (kTile + 8) * 4;              // int32[NGRP + 1] (+pad)
   static constexpr int kCj = kCi + ((NGRP + 1 + 3) / 4) * 16;      // int32[NGRP + 1] (+pad)
   static constexpr int kFlag = kCj + ((NGRP + 1 + 3) / 4) * 16;    // int32[NGRP] (+pad)
@@ -240,7 +240,7 @@ struct TileSmem {
 // PEER: the epilogue also stores every finished row to the peers' replicas / the multicast address.
 template <int G, int CH, int MODE, bool EPI, bool PEER>
 __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2)) gather_tiled_kernel(const __grid_constant__ GatherArgs a) {
-  using L = TileSmem<G, CH>;
+  using L = TileSmem<G, CH, MODE != 0>;
   constexpr int NGRP = L::NGRP;
   constexpr int U = (CH == 1) ? 8 : (CH == 2 ? 4 : 2);
   extern __shared__ __align__(16) unsigned char smem[];
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
   const int64_t e0 = __ldg(a.tile_edge + k), e1 = __ldg(a.tile_edge + k + 1);
   const int nr = int(r1 - r0);  // rows whose end falls inside the tile
   const int ne = int(e1 - e0);  // edges inside the tile
-  const bool has_val = a.val != nullptr;
+  const bool has_val = (MODE != 0) && a.val != nullptr;
 
   // ---- stage the CSR slice: TMA bulk copy for col/val, plain loads for the row ends ----
   const int64_t e0a = e0 & ~int64_t(3);  // 16-byte aligned start
@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(kThreads) tile_fixup_kernel(const __grid_const
 // ---------------------------------------------------------------------------
 template <int G, int CH, int MODE, bool EPI, bool PEER>
 static int launch_tiled(const GatherArgs& a, cudaStream_t st) {
-  using L = TileSmem<G, CH>;
+  using L = TileSmem<G, CH, MODE != 0>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
     GGAD_CUDA_OK(cudaFuncSetAttribute(gather_tiled_kernel<G, CH, MODE, EPI, PEER>,

@@ -36,7 +36,9 @@ extern "C" {
 #define GGAD_ERR_CUDA (-3)        /* CUDA runtime error (message in ggad_last_error) */
 #define GGAD_ERR_UNSUPPORTED (-4) /* width or size outside what the kernels cover */
 
+#ifndef GGAD_TILE_ITEMS
 #define GGAD_TILE_ITEMS 2048 /* merge-path items (rows + edges) per CTA tile */
+#endif
 #define GGAD_MAX_WIDTH 768   /* max logical width d per launch (745 pads to 748) */
 
 typedef void* ggad_stream_t;
