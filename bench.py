@@ -343,7 +343,7 @@ def e2e_leg(args, world, rank, dev, fwd, bwd, fr, br, value):
     d = args.width
     n_local = args.nodes
     n_glob = n_local * world
-    steps = max(2, min(args.steps, 5))
+    steps = max(2, min(args.steps, 10))
     lo_b, hi_b = br[rank]
     x_host = torch.randn(n_local, d).pin_memory()
     dx_host = torch.empty(hi_b - lo_b, d).pin_memory()
@@ -359,18 +359,33 @@ def e2e_leg(args, world, rank, dev, fwd, bwd, fr, br, value):
             r.tile_row, r.tile_edge, r.n_tiles = ptr(p[0]), ptr(p[1]), p[2]
             return r
         ra, rt = res(fwd), res(bwd)
-        bufs = [torch.empty(n_local, d, device=dev) for _ in range(3)]
-        ws = torch.empty(2 * max(ra.n_tiles, rt.n_tiles) * d + n_local + 16, device=dev)
-        loss = C.c_double(0)
-        for i in range(steps + 1):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            _lib.check(lib.ggad_spmm_fwd_bwd_host(C.byref(ra), C.byref(rt), ptr(x_host), None, ptr(dx_host),
-                                                  C.addressof(loss), d, ptr(bufs[0]), ptr(bufs[1]), ptr(bufs[2]), ptr(ws),
-                                                  _lib.stream_ptr(dev)))
-            if i:
-                times.append(time.perf_counter() - t0)
-        api = "ggad_spmm_fwd_bwd_host (C ABI, pinned host buffers)"
+        # two pipeline slots (own stream + device scratch + pinned result buffers): the H2D of step i+1 overlaps
+        # the D2H of step i; every step still copies its features in and its gradient + loss out
+        n_slots = 2
+        slots = []
+        for _ in range(n_slots):
+            slots.append(dict(stream=torch.cuda.Stream(device=dev),
+                              bufs=[torch.empty(n_local, d, device=dev) for _ in range(3)],
+                              ws=torch.empty(2 * max(ra.n_tiles, rt.n_tiles) * d + n_local + 16, device=dev),
+                              dx=torch.empty(hi_b - lo_b, d).pin_memory(),
+                              loss=torch.zeros(1, dtype=torch.float64).pin_memory()))
+        torch.cuda.synchronize()
+
+        def enqueue(i):
+            s = slots[i % n_slots]
+            _lib.check(lib.ggad_spmm_fwd_bwd_host_enqueue(C.byref(ra), C.byref(rt), ptr(x_host), None, ptr(s["dx"]),
+                                                          ptr(s["loss"]), d, ptr(s["bufs"][0]), ptr(s["bufs"][1]),
+                                                          ptr(s["bufs"][2]), ptr(s["ws"]), s["stream"].cuda_stream))
+        for i in range(2):                      # warm-up
+            enqueue(i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            enqueue(i)
+        torch.cuda.synchronize()
+        times = [(time.perf_counter() - t0) / steps]
+        assert all(float(s["loss"][0]) > 0 for s in slots)
+        api = "ggad_spmm_fwd_bwd_host_enqueue (C ABI, pinned host buffers, 2 pipelined streams)"
     else:
         x_full = torch.empty(n_glob, d, device=dev)
         y_full = torch.empty(n_glob, d, device=dev)

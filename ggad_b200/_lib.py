@@ -66,6 +66,8 @@ SIGNATURES = {
     "ggad_rmat_keys": (C.c_int, [_vp, _i64, _i64, _i32, _i32, C.c_uint64, _f, _f, _f, _i64, _i64, _vp, _vp]),
     "ggad_spmm_fwd_bwd_host": (C.c_int, [C.POINTER(ResidentCSR), C.POINTER(ResidentCSR), _vp, _vp, _vp, _vp, _i32,
                                          _vp, _vp, _vp, _vp, _vp]),
+    "ggad_spmm_fwd_bwd_host_enqueue": (C.c_int, [C.POINTER(ResidentCSR), C.POINTER(ResidentCSR), _vp, _vp, _vp, _vp, _i32,
+                                                 _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

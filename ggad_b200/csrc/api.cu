@@ -81,7 +81,7 @@ static void fill_desc(ggad_gather_desc_t& g, const ggad_resident_csr_t* m, const
 
 int spmm_fwd_bwd_host_impl(const ggad_resident_csr_t* a, const ggad_resident_csr_t* at, const float* x_host, float* y_host,
                            float* dx_host, double* loss_host, int32_t d, float* dev_x, float* dev_y, float* dev_dx,
-                           float* dev_ws, cudaStream_t st) {
+                           float* dev_ws, cudaStream_t st, bool sync) {
   GGAD_REQUIRE(a && at && x_host && dx_host && dev_x && dev_y && dev_dx && dev_ws, GGAD_ERR_INVALID, "spmm_fwd_bwd_host: null pointer");
   GGAD_REQUIRE(a->n_rows == at->n_cols && a->n_cols == at->n_rows && a->nnz == at->nnz, GGAD_ERR_INVALID,
                "spmm_fwd_bwd_host: at is not the transpose shape of a");
@@ -103,6 +103,10 @@ int spmm_fwd_bwd_host_impl(const ggad_resident_csr_t* a, const ggad_resident_csr
   rc = gather_reduce_impl(&g, st);
   if (rc != GGAD_OK) return rc;
   GGAD_CUDA_OK(cudaMemcpyAsync(dx_host, dev_dx, xin, cudaMemcpyDeviceToHost, st));
+  if (!sync) {  // enqueue only: loss_host must be pinned, the caller synchronises the stream
+    if (loss_host) GGAD_CUDA_OK(cudaMemcpyAsync(loss_host, dev_loss, 8, cudaMemcpyDeviceToHost, st));
+    return GGAD_OK;
+  }
   double h = 0.0;
   GGAD_CUDA_OK(cudaMemcpyAsync(&h, dev_loss, 8, cudaMemcpyDeviceToHost, st));
   GGAD_CUDA_OK(cudaStreamSynchronize(st));
@@ -209,7 +213,14 @@ GGAD_API int ggad_spmm_fwd_bwd_host(const ggad_resident_csr_t* a, const ggad_res
                            float* dx_host, double* loss_host, int32_t d, float* dev_x, float* dev_y, float* dev_dx,
                            float* dev_ws, ggad_stream_t stream) {
   return spmm_fwd_bwd_host_impl(a, at, x_host, y_host, dx_host, loss_host, d, dev_x, dev_y, dev_dx, dev_ws,
-                                (cudaStream_t)stream);
+                                (cudaStream_t)stream, true);
+}
+
+GGAD_API int ggad_spmm_fwd_bwd_host_enqueue(const ggad_resident_csr_t* a, const ggad_resident_csr_t* at, const float* x_host,
+                                            float* y_host, float* dx_host, double* loss_host, int32_t d, float* dev_x,
+                                            float* dev_y, float* dev_dx, float* dev_ws, ggad_stream_t stream) {
+  return spmm_fwd_bwd_host_impl(a, at, x_host, y_host, dx_host, loss_host, d, dev_x, dev_y, dev_dx, dev_ws,
+                                (cudaStream_t)stream, false);
 }
 
 }  // extern "C"

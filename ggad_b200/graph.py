@@ -226,7 +226,7 @@ class AdjListCSR:
     """Host CSR view of the ``dict[int -> set[int]]`` adjacency lists of program B
     (src/utils.py:27-28,96-112), built once; neighbor ids sorted."""
 
-    _cache: Dict[int, "AdjListCSR"] = {}
+    _cache: Dict[int, tuple] = {}
 
     def __init__(self, adj_lists, n: Optional[int] = None):
         keys = np.fromiter((int(k) for k in adj_lists.keys()), dtype=np.int64)
@@ -257,14 +257,15 @@ class AdjListCSR:
 
     @classmethod
     def get(cls, adj_lists) -> "AdjListCSR":
+        """Cached conversion of a dict-of-sets adjacency (the cache keeps a reference to the dict)."""
         key = id(adj_lists)
         hit = cls._cache.get(key)
-        if hit is None or hit.n_keys != len(adj_lists):
-            hit = cls(adj_lists)
+        if hit is None or hit[0] is not adj_lists or hit[1].n_keys != len(adj_lists):
+            hit = (adj_lists, cls(adj_lists))
             if len(cls._cache) > 4:
                 cls._cache.clear()
             cls._cache[key] = hit
-        return hit
+        return hit[1]
 
     def neighbors(self, nodes: np.ndarray, add_self: bool):
         """Block (rows=len(nodes)) -> (rowptr, col_global) with per-row sorted unique neighbor ids

@@ -49,13 +49,11 @@ def _feature_table(features) -> Optional[torch.Tensor]:
     w = features.weight
     if not w.is_cuda:
         raise RuntimeError("ggad_b200: move the feature table to a CUDA device (features.cuda()); no CPU fallback")
-    key = (id(w), w._version, w.data_ptr())
-    t = _table_cache.get(key)
-    if t is None:
-        t = ops.pad_cols(w.detach())
-        _table_cache.clear()
-        _table_cache[key] = t
-    return t
+    hit = _table_cache.get("t")
+    if hit is None or hit[0] is not w or hit[1] != (w._version, w.data_ptr(), tuple(w.shape)):
+        hit = (w, (w._version, w.data_ptr(), tuple(w.shape)), ops.pad_cols(w.detach()))
+        _table_cache["t"] = hit           # one table at a time; the entry keeps `w` alive, so no id recycling
+    return hit[2]
 
 
 class _Block:

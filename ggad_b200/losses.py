@@ -17,18 +17,21 @@ _subset_cache = {}
 
 
 def _subset(normal_idx, abnormal_idx, device):
-    """Unique union of the two index lists + positions of each list inside it (cached on identity)."""
-    key = (id(normal_idx), len(normal_idx), id(abnormal_idx), len(abnormal_idx), str(device))
+    """Unique union of the two index lists + positions of each list inside it.  Cached per list objects (the
+    cache holds references, so ids cannot be recycled under it)."""
+    key = (id(normal_idx), id(abnormal_idx), str(device))
     hit = _subset_cache.get(key)
-    if hit is None:
+    if (hit is None or hit[0] is not normal_idx or hit[1] is not abnormal_idx
+            or hit[2] != (len(normal_idx), len(abnormal_idx))):
         n, a = np.asarray(normal_idx, dtype=np.int64), np.asarray(abnormal_idx, dtype=np.int64)
         uniq, inv = np.unique(np.concatenate([n, a]), return_inverse=True)
-        hit = (torch.from_numpy(uniq.astype(np.int32)).to(device),
+        val = (torch.from_numpy(uniq.astype(np.int32)).to(device),
                torch.from_numpy(inv[:len(n)]).to(device), torch.from_numpy(inv[len(n):]).to(device))
+        hit = (normal_idx, abnormal_idx, (len(normal_idx), len(abnormal_idx)), val)
         if len(_subset_cache) > 8:
             _subset_cache.clear()
         _subset_cache[key] = hit
-    return hit
+    return hit[3]
 
 
 def ggad_loss(emb, logits, emb_con, emb_abnormal, raw_adj, normal_label_idx, abnormal_label_idx,

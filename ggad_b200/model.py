@@ -23,34 +23,41 @@ _graph_cache = {}
 _index_cache = {}
 
 
+def _probe(idx):
+    n = len(idx)
+    return (n, idx[0], idx[n // 2], idx[-1]) if n else (0,)
+
+
 def _device_index(idx, device) -> torch.Tensor:
-    """LongTensor copy of a Python index list on the device, cached on the list's identity so that the
-    forward pass issues no host->device copies (required for CUDA-graph capture)."""
+    """LongTensor copy of a Python index list on the device.  Cached per list OBJECT (the cache keeps a
+    reference, so an id can never be recycled while its entry is alive) so that the forward pass issues no
+    host->device copies -- required for CUDA-graph capture."""
     if isinstance(idx, torch.Tensor):
         return idx.to(device=device, dtype=torch.long)
-    key = (id(idx), len(idx), str(device))
+    key = (id(idx), str(device))
     hit = _index_cache.get(key)
-    if hit is None or hit[1] != (idx[0] if len(idx) else None, idx[-1] if len(idx) else None):
+    if hit is None or hit[0] is not idx or hit[2] != _probe(idx):
         t = torch.as_tensor(list(idx), dtype=torch.long).to(device)
-        hit = (t, (idx[0] if len(idx) else None, idx[-1] if len(idx) else None))
+        hit = (idx, t, _probe(idx))
         if len(_index_cache) > 16:
             _index_cache.clear()
         _index_cache[key] = hit
-    return hit[0]
+    return hit[1]
 
 
 def as_graph(adj, device) -> CSRGraph:
     """Convert whatever run.py hands over into a (cached) CSRGraph."""
     if isinstance(adj, CSRGraph):
         return adj
-    key = (id(adj), getattr(adj, "_version", None), str(device))
-    g = _graph_cache.get(key)
-    if g is None:
-        g = CSRGraph.from_any(adj, device)
+    key = (id(adj), str(device))
+    hit = _graph_cache.get(key)
+    version = getattr(adj, "_version", None)
+    if hit is None or hit[0] is not adj or hit[1] != version:
+        hit = (adj, version, CSRGraph.from_any(adj, device))
         if len(_graph_cache) > 8:
             _graph_cache.clear()
-        _graph_cache[key] = g
-    return g
+        _graph_cache[key] = hit
+    return hit[2]
 
 
 class GCN(nn.Module):

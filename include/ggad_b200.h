@@ -208,6 +208,13 @@ typedef struct ggad_resident_csr {
 GGAD_API int ggad_spmm_fwd_bwd_host(const ggad_resident_csr_t* a, const ggad_resident_csr_t* at, const float* x_host,
                            float* y_host, float* dx_host, double* loss_host, int32_t d, float* dev_x, float* dev_y,
                            float* dev_dx, float* dev_ws, ggad_stream_t stream);
+/* Same work, enqueued only (no synchronisation): all host buffers incl. loss_host must be pinned.  Calls
+ * on different streams with their own dev_* scratch overlap one step's H2D with the previous step's D2H
+ * (PCIe is full duplex), which is how a training loop would pipeline host-fed batches. */
+GGAD_API int ggad_spmm_fwd_bwd_host_enqueue(const ggad_resident_csr_t* a, const ggad_resident_csr_t* at,
+                                            const float* x_host, float* y_host, float* dx_host, double* loss_host,
+                                            int32_t d, float* dev_x, float* dev_y, float* dev_dx, float* dev_ws,
+                                            ggad_stream_t stream);
 
 #ifdef __cplusplus
 }

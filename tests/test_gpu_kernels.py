@@ -360,6 +360,20 @@ def test_host_buffer_entry_point():
     dx = ops.gather_reduce(gt, y)["y"]
     assert torch.equal(y.cpu(), y_h) and torch.equal(dx.cpu(), dx_h)
     assert abs(loss.value - 0.5 * float((y.double() ** 2).sum())) <= 1e-6 * loss.value + 1e-6
+    # enqueue-only variant on two side streams (pipelined steps): same bits, pinned loss slots
+    torch.cuda.synchronize()
+    outs = []
+    for i in range(2):
+        st = torch.cuda.Stream()
+        o = dict(dx=torch.empty(n, d).pin_memory(), loss=torch.zeros(1, dtype=torch.float64).pin_memory(),
+                 dev=[torch.empty(n, d, device="cuda") for _ in range(3)], ws=torch.empty_like(ws), st=st)
+        check(lib.ggad_spmm_fwd_bwd_host_enqueue(C.byref(ra), C.byref(rt), ptr(x), None, ptr(o["dx"]), ptr(o["loss"]), d,
+                                                 ptr(o["dev"][0]), ptr(o["dev"][1]), ptr(o["dev"][2]), ptr(o["ws"]),
+                                                 st.cuda_stream))
+        outs.append(o)
+    torch.cuda.synchronize()
+    for o in outs:
+        assert torch.equal(o["dx"], dx_h) and float(o["loss"][0]) == loss.value
 
 
 def test_errors_are_loud():
