@@ -5,8 +5,9 @@
 
 Workload (config.workload): ``S64`` = one C5 shard per GPU -- 6.25 M nodes / 125 M edges / d = 64 per GPU
 (at N = 8 this is BASELINE.json's 50 M-node / 1 B-edge graph) -- weak scaling.  A step is
-    Y  = A[lo:hi, :] X          (mean aggregation over the rank's destination range), replicated to all ranks
-                                (N>1: NVLink P2P stores fused into the gather epilogue, or NCCL all-gather)
+    Y  = A[lo:hi, :] X          (mean aggregation over the rank's destination range), delivered to the ranks
+                                whose backward shard gathers it (N>1: NVLink P2P stores fused into the gather
+                                epilogue -- only the halo rows by default -- or a plain NCCL all-gather)
     dX[lo':hi'] = A^T[lo':hi', :] dY   (dY = Y, loss = |Y|^2/2; transposed CSR rows, no atomics; stays sharded)
 `value` = total edges of all ranks / step time with everything resident in HBM (inputs >> L2, so no flush
 is needed); `e2e` = same pass with the features coming from pinned host memory and dX + loss read back,
@@ -208,7 +209,8 @@ def native(args):
     # peer memory (P2P stores or NVSwitch multicast), or a plain NCCL all-gather
     exchange = args.exchange if world > 1 else "none"
     rep = None
-    if exchange in ("fused", "multicast"):
+    need, halo_frac = None, None
+    if exchange in ("halo", "fused", "multicast"):
         try:
             rep = gdist.PeerReplica(n_glob, d, fr, rank, dev)
             if exchange == "multicast" and not rep.multicast_ptr:
@@ -217,6 +219,14 @@ def native(args):
             if rank == 0:
                 print(f"[bench] symmetric memory unavailable ({e}); using NCCL all-gather", file=sys.stderr)
             exchange, rep = "nccl", None
+    if exchange == "halo":
+        # rows of this rank's Y shard that peer p's backward shard gathers (distinct columns of its A^T rows)
+        need = gdist.halo_need_mask(bwd.col, fr, rank)
+        sent = torch.zeros(1, dtype=torch.int64, device=dev)
+        for s_ in range(world - 1):
+            sent += ((need >> s_) & 1).sum()
+        dist.all_reduce(sent)
+        halo_frac = float(sent.item()) / (n_glob * (world - 1))
 
     def step(ev=None):
         if exchange == "none":
@@ -236,6 +246,8 @@ def native(args):
             rep.barrier(0)                       # peers finished reading the previous Y
             if exchange == "multicast":
                 ops.gather_reduce(fwd, x, y_out=rep.local_rows, y_multicast=rep.multicast_row_ptr)
+            elif exchange == "halo":
+                ops.gather_reduce(fwd, x, y_out=rep.local_rows, y_peers=rep.peer_row_ptrs, peer_need=need)
             else:
                 ops.gather_reduce(fwd, x, y_out=rep.local_rows, y_peers=rep.peer_row_ptrs)
             if ev:
@@ -323,7 +335,8 @@ def native(args):
             "config": {"workload": args.workload, "nodes_per_gpu": n_local, "edges_per_gpu": m_local, "width": d,
                        "global_nodes": n_glob, "global_edges": total_edges, "aggregation": "mean (row_scale = 1/deg)",
                        "l2": "inputs larger than L2 (no flush)" if n_glob * d * 4 > 2e8 else "L2-resident operand (no flush)",
-                       "parallelism": f"dst-node-range x{world}, exchange={exchange}", "graph_build_s": round(t_build, 2)},
+                       "parallelism": f"dst-node-range x{world}, exchange={exchange}", "graph_build_s": round(t_build, 2),
+                       "halo_rows_sent_frac": halo_frac},
             "segments_ms": {"fwd_compute": float(seg_mean[0]), "fwd_exchange": float(seg_mean[1]),
                             "bwd_compute": float(seg_mean[2]), "bwd_exchange": float(seg_mean[3])},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -446,8 +459,10 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--rmat", default=None, help="a,b,c of the R-MAT generator (default 0.57,0.19,0.19); 0.25,0.25,0.25 = uniform")
     ap.add_argument("--cpu-frac", type=int, default=8, help="CPU legs run on 1/frac of the per-GPU workload")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "multicast", "nccl"],
-                    help="N>1: how the forward output is replicated (fused = NVLink P2P stores from the gather epilogue)")
+    ap.add_argument("--exchange", default="halo", choices=["halo", "fused", "multicast", "nccl"],
+                    help="N>1: how the forward output reaches the ranks that gather it next.  halo = NVLink P2P stores "
+                         "from the gather epilogue, only rows a peer's next pass reads; fused = same, every row to every "
+                         "peer; multicast = one NVSwitch multimem.st per row; nccl = separate all-gather")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

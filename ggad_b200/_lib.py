@@ -30,7 +30,7 @@ class GatherDesc(C.Structure):
         ("sumsq", _vp), ("dot_mat", _vp), ("lddot", C.c_int64), ("dot_rows", _vp), ("dot_scale", _vp),
         ("dot_out", _vp),
         ("tile_row", _vp), ("tile_edge", _vp), ("n_tiles", C.c_int64), ("ws", _vp),
-        ("y_peer", _vp * 7), ("n_peer", C.c_int32), ("reserved", C.c_int32), ("y_multicast", _vp),
+        ("y_peer", _vp * 7), ("n_peer", C.c_int32), ("reserved", C.c_int32), ("y_multicast", _vp), ("peer_need", _vp),
     ]
 
 

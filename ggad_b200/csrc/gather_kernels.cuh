@@ -52,6 +52,7 @@ struct GatherArgs {
   float* y_peer[7];
   int n_peer;
   float* y_mc;
+  const uint32_t* peer_need;
 };
 
 constexpr int kThreads = 256;
@@ -75,7 +76,10 @@ __device__ __forceinline__ void store_y(const GatherArgs& a, int64_t r, int ch, 
     return;
   }
   if (a.y) stg_cs_f4(reinterpret_cast<float4*>(a.y + off), v);
-  for (int p = 0; p < a.n_peer; ++p) stg_cs_f4(reinterpret_cast<float4*>(a.y_peer[p] + off), v);
+  // halo exchange: only the peers whose next pass gathers this row receive it
+  const uint32_t need = a.peer_need ? __ldg(a.peer_need + r) : 0xffffffffu;
+  for (int p = 0; p < a.n_peer; ++p)
+    if ((need >> p) & 1u) stg_cs_f4(reinterpret_cast<float4*>(a.y_peer[p] + off), v);
   if (a.y_mc) {
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.y_mc + off), "f"(v.x), "f"(v.y),
                  "f"(v.z), "f"(v.w)

@@ -88,6 +88,9 @@ int gather_reduce_impl(const ggad_gather_desc_t* d, cudaStream_t st) {
     GGAD_REQUIRE(p >= d->n_peer || (a.y_peer[p] && aligned16(a.y_peer[p])), GGAD_ERR_ALIGN, "gather_reduce: y_peer[%d] null or unaligned", p);
   }
   a.y_mc = d->y_multicast;
+  a.peer_need = d->peer_need;
+  GGAD_REQUIRE(!a.peer_need || (d->n_peer > 0 && !a.y_mc), GGAD_ERR_INVALID,
+               "gather_reduce: peer_need needs y_peer[] and excludes y_multicast");
   GGAD_REQUIRE(aligned16(a.y_mc), GGAD_ERR_ALIGN, "gather_reduce: y_multicast not 16-byte aligned");
   const int sms = sm_count_cached();
   if (sms <= 0) return GGAD_ERR_CUDA;

@@ -76,6 +76,38 @@ def all_gather_rows(local: torch.Tensor, ranges: Sequence[Tuple[int, int]], out:
     return out
 
 
+def halo_need_mask(consumer_col: torch.Tensor, ranges: Sequence[Tuple[int, int]], rank: int, group=None,
+                   chunk: int = 1 << 26) -> torch.Tensor:
+    """Which peers gather which of this rank's rows in their next pass (the halo of a layer exchange).
+
+    ``consumer_col`` is the column array of the CSR shard THIS rank runs next on the replicated matrix (the
+    backward's A^T rows, or the next layer's A rows); its distinct columns are the only rows of the
+    replica this rank will ever read.  Every rank marks them, the marks are exchanged once, and the owner of
+    rows [lo, hi) gets an int32 mask per owned row: bit s set <=> the s-th peer (ranks != ``rank`` in
+    ascending order, the order of PeerReplica.peer_row_ptrs) needs that row.  Pure integer work, exact, and
+    backend-agnostic (tested on CPU with gloo)."""
+    world = len(ranges)
+    n = ranges[-1][1]
+    dev = consumer_col.device
+    need = torch.zeros(n, dtype=torch.uint8, device=dev)
+    one = torch.ones((), dtype=torch.uint8, device=dev)
+    for part in consumer_col.split(chunk):
+        need.index_put_((part.long(),), one)
+    lo, hi = ranges[rank]
+    mask = torch.zeros(hi - lo, dtype=torch.int32, device=dev)
+    if world == 1:
+        return mask
+    marks = [torch.empty_like(need) for _ in range(world)]
+    dist.all_gather(marks, need, group=group)
+    slot = 0
+    for r in range(world):
+        if r == rank:
+            continue
+        mask |= marks[r][lo:hi].to(torch.int32) << slot
+        slot += 1
+    return mask
+
+
 class PeerReplica:
     """A replicated [N, d] fp32 matrix in CUDA symmetric memory (one copy per rank, peer-mapped over NVLink).
 

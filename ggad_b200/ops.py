@@ -35,7 +35,8 @@ def gather_reduce(g: CSRGraph, x: torch.Tensor, *, xmap: Optional[torch.Tensor] 
                   want_y: bool = True, want_z: bool = False, want_sumsq: bool = False,
                   dot_mat: Optional[torch.Tensor] = None, dot_rows: Optional[torch.Tensor] = None,
                   dot_scale: Optional[torch.Tensor] = None, use_graph_scales: bool = True,
-                  y_out: Optional[torch.Tensor] = None, y_peers=None, y_multicast: Optional[int] = None):
+                  y_out: Optional[torch.Tensor] = None, y_peers=None, y_multicast: Optional[int] = None,
+                  peer_need: Optional[torch.Tensor] = None):
     """Raw (non-autograd) call of ggad_gather_reduce.  ``x`` is [n_x_rows, d] fp32 CUDA with d % 4 == 0.
     Returns dict(y=, z=, sumsq=, dot=) with the requested outputs."""
     _lib.require_cuda(x, "x")
@@ -73,6 +74,9 @@ def gather_reduce(g: CSRGraph, x: torch.Tensor, *, xmap: Optional[torch.Tensor] 
         for i, pp in enumerate(y_peers):
             desc.y_peer[i] = int(pp)
         desc.n_peer = len(y_peers)
+        if peer_need is not None:     # halo exchange: int32 bit mask per row, bit p = y_peers[p] gathers the row
+            assert peer_need.dtype == torch.int32 and peer_need.numel() == n and peer_need.is_cuda
+            desc.peer_need = ptr(peer_need)
     if y_multicast:
         desc.y_multicast = int(y_multicast)
         desc.y = None

@@ -120,6 +120,10 @@ typedef struct ggad_gather_desc {
   int32_t n_peer;
   int32_t reserved;
   float* y_multicast; /* NULL or multicast address covering all ranks (replaces y and y_peer) */
+  /* halo exchange: NULL (every row goes to every peer) or [n_rows] bit masks -- bit p set means y_peer[p]
+   * gathers row r in its next pass (the row is a column of that peer's CSR shard), so only those rows
+   * cross NVLink.  Rows a peer does not need are left untouched in its replica. */
+  const uint32_t* peer_need;
 } ggad_gather_desc_t;
 
 GGAD_API int ggad_gather_reduce(const ggad_gather_desc_t* desc, ggad_stream_t stream);

@@ -16,7 +16,7 @@ def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     import scipy.sparse as sp
     import oracle
-    from ggad_b200.dist import ShardedLayerPass, nnz_balanced_ranges
+    from ggad_b200.dist import ShardedLayerPass, halo_need_mask, nnz_balanced_ranges
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -49,6 +49,16 @@ def _worker(rank, world, port, q):
     gathered = [torch.empty_like(dx) for _ in range(world)]
     dist.all_gather(gathered, dx)
     ok = ok and all(torch.equal(gathered[0], t) for t in gathered)
+    # halo masks (integer, exact): bit s of mask[r] <=> the s-th peer's backward shard has row lo+r as a column
+    mask = halo_need_mask(torch.from_numpy(shard(at, *br[rank])[1]), fr, rank)
+    lo, hi = fr[rank]
+    peers = [r for r in range(world) if r != rank]
+    expect = np.zeros(hi - lo, np.int32)
+    for s, p in enumerate(peers):
+        cols = np.unique(shard(at, *br[p])[1])
+        cols = cols[(cols >= lo) & (cols < hi)] - lo
+        expect[cols] |= 1 << s
+    ok = ok and mask.dtype == torch.int32 and np.array_equal(mask.numpy(), expect) and 0 < int((expect != 0).sum())
     q.put((rank, bool(ok), fr, br))
     dist.destroy_process_group()
 

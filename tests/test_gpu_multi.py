@@ -57,8 +57,25 @@ def _worker(rank, world, port, q):
         ops.gather_reduce(fwd, x, y_out=rep.local_rows, y_multicast=rep.multicast_row_ptr)
         rep.barrier(0)
         mc_ok = torch.equal(rep.buf, y)
-    ok = fused_ok and mc_ok
-    msg = f"fused={fused_ok} multicast={'n/a' if not rep.multicast_ptr else mc_ok} "
+    # halo exchange: only rows some peer's backward shard gathers cross NVLink.  Needed rows must be bit-identical
+    # to the all-gather, rows nobody asked for must be left untouched (poisoned first), and the backward on the
+    # halo replica must be bit-identical to the backward on the full replica
+    need = gdist.halo_need_mask(bwd.col, fr, rank)
+    rep.barrier(0)
+    rep.buf.fill_(float("nan"))
+    rep.barrier(1)
+    ops.gather_reduce(fwd, x, y_out=rep.local_rows, y_peers=rep.peer_row_ptrs, peer_need=need)
+    rep.barrier(0)
+    mine = torch.zeros(n_glob, dtype=torch.bool, device=dev)
+    mine[bwd.col.long()] = True
+    mine[fr[rank][0]:fr[rank][1]] = True
+    halo_ok = torch.equal(rep.buf[mine], y[mine]) and bool(torch.isnan(rep.buf[~mine]).all())
+    dx_halo = ops.gather_reduce(bwd, rep.buf)["y"]
+    halo_ok = halo_ok and torch.equal(dx_halo, dx[lo:hi])
+    frac = float((need != 0).float().mean())
+    rep.barrier(1)
+    ok = fused_ok and mc_ok and halo_ok
+    msg = f"fused={fused_ok} multicast={'n/a' if not rep.multicast_ptr else mc_ok} halo={halo_ok} (rows sent {frac:.2f}) "
     if rank == 0:
         # single-GPU reference on the concatenated graph, same kernels
         parts = [synth.rmat_shard(n_local, m_local, world, s, seed=seed, device=dev, mean=True) for s in range(world)]
