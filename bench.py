@@ -186,7 +186,7 @@ def native(args):
         dist.all_reduce(cnt)
         rowptr_t = torch.zeros(n_glob + 1, dtype=torch.int64, device=dev)
         torch.cumsum(cnt, 0, out=rowptr_t[1:])
-        br = gdist.nnz_balanced_ranges(rowptr_t.cpu().numpy(), world)
+        br = gdist.nnz_balanced_ranges(rowptr_t.cpu().numpy(), world, row_cost=args.row_cost)   # balance rows + edges
         del cnt, rowptr_t
         rs_all = torch.empty(n_glob, dtype=torch.float32, device=dev)
         dist.all_gather_into_tensor(rs_all, fwd.row_scale)
@@ -227,6 +227,12 @@ def native(args):
             sent += ((need >> s_) & 1).sum()
         dist.all_reduce(sent)
         halo_frac = float(sent.item()) / (n_glob * (world - 1))
+    peer_ptrs = rep.peer_row_ptrs if rep is not None else None
+    if args.peer_debug == "zero_mask":          # diagnostics: PEER kernel variant, nothing crosses NVLink
+        need = torch.zeros(n_local, dtype=torch.int32, device=dev)
+    elif args.peer_debug == "local_peers":      # diagnostics: the peer stores land in a local scratch matrix
+        scratch = torch.empty(n_local, d, device=dev)
+        peer_ptrs = [scratch.data_ptr()] * (world - 1)
 
     def step(ev=None):
         if exchange == "none":
@@ -247,9 +253,9 @@ def native(args):
             if exchange == "multicast":
                 ops.gather_reduce(fwd, x, y_out=rep.local_rows, y_multicast=rep.multicast_row_ptr)
             elif exchange == "halo":
-                ops.gather_reduce(fwd, x, y_out=rep.local_rows, y_peers=rep.peer_row_ptrs, peer_need=need)
+                ops.gather_reduce(fwd, x, y_out=rep.local_rows, y_peers=peer_ptrs, peer_need=need)
             else:
-                ops.gather_reduce(fwd, x, y_out=rep.local_rows, y_peers=rep.peer_row_ptrs)
+                ops.gather_reduce(fwd, x, y_out=rep.local_rows, y_peers=peer_ptrs, peer_need=need)
             if ev:
                 ev[1].record()
             rep.barrier(1)                       # every shard has landed in every replica
@@ -293,6 +299,18 @@ def native(args):
     ms_per_step = float(tt.item()) / args.steps
     seg = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in evs])   # fwd, xchg, bwd, xchg
     seg_mean = seg.mean(0)
+    shard_stats = [[bwd.n_rows, bwd.nnz]]
+    if world > 1:
+        st_ = [None] * world
+        dist.all_gather_object(st_, [bwd.n_rows, bwd.nnz])
+        shard_stats = st_
+    seg_all = torch.tensor(seg_mean, dtype=torch.float64, device=dev)
+    if world > 1:
+        gl = [torch.empty_like(seg_all) for _ in range(world)]
+        dist.all_gather(gl, seg_all)
+        seg_ranks = [[round(float(v), 3) for v in t.tolist()] for t in gl]
+    else:
+        seg_ranks = [[round(float(v), 3) for v in seg_mean]]
     total_edges = m_local * world
     value = total_edges / (ms_per_step * 1e-3)
 
@@ -336,9 +354,11 @@ def native(args):
                        "global_nodes": n_glob, "global_edges": total_edges, "aggregation": "mean (row_scale = 1/deg)",
                        "l2": "inputs larger than L2 (no flush)" if n_glob * d * 4 > 2e8 else "L2-resident operand (no flush)",
                        "parallelism": f"dst-node-range x{world}, exchange={exchange}", "graph_build_s": round(t_build, 2),
-                       "halo_rows_sent_frac": halo_frac},
+                       "halo_rows_sent_frac": halo_frac, "bwd_ranges": [list(map(int, r)) for r in br],
+                       "bwd_shard_rows_nnz": shard_stats},
             "segments_ms": {"fwd_compute": float(seg_mean[0]), "fwd_exchange": float(seg_mean[1]),
-                            "bwd_compute": float(seg_mean[2]), "bwd_exchange": float(seg_mean[3])},
+                            "bwd_compute": float(seg_mean[2]), "bwd_exchange": float(seg_mean[3]),
+                            "per_rank": seg_ranks},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(out), flush=True)
@@ -463,6 +483,10 @@ def main():
                     help="N>1: how the forward output reaches the ranks that gather it next.  halo = NVLink P2P stores "
                          "from the gather epilogue, only rows a peer's next pass reads; fused = same, every row to every "
                          "peer; multicast = one NVSwitch multimem.st per row; nccl = separate all-gather")
+    ap.add_argument("--row-cost", type=int, default=3,
+                    help="N>1: cost of one output row in edges when the backward ranges are balanced")
+    ap.add_argument("--peer-debug", default=None, choices=["zero_mask", "local_peers"],
+                    help="diagnostics only (results are NOT exchanged): isolate the cost of the peer stores")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

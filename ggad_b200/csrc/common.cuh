@@ -74,6 +74,20 @@ __device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
 // streaming (evict-first) 128-bit store for outputs that are not re-read by this kernel
 __device__ __forceinline__ void stg_cs_f4(float4* p, const float4& v) { __stcs(p, v); }
 
+// 128-bit store into a peer GPU's memory over NVLink (A/B knob: GGAD_PEER_ST = 0 plain, 1 streaming, 2 write-through)
+#ifndef GGAD_PEER_ST
+#define GGAD_PEER_ST 1
+#endif
+__device__ __forceinline__ void stg_peer_f4(float4* p, const float4& v) {
+#if GGAD_PEER_ST == 0
+  *p = v;
+#elif GGAD_PEER_ST == 2
+  __stwt(p, v);
+#else
+  __stcs(p, v);
+#endif
+}
+
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ void f4_fma(float4& a, float w, const float4& x) {
   a.x = fmaf(w, x.x, a.x);

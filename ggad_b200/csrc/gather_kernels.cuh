@@ -79,7 +79,7 @@ __device__ __forceinline__ void store_y(const GatherArgs& a, int64_t r, int ch, 
   // halo exchange: only the peers whose next pass gathers this row receive it
   const uint32_t need = a.peer_need ? __ldg(a.peer_need + r) : 0xffffffffu;
   for (int p = 0; p < a.n_peer; ++p)
-    if ((need >> p) & 1u) stg_cs_f4(reinterpret_cast<float4*>(a.y_peer[p] + off), v);
+    if ((need >> p) & 1u) stg_peer_f4(reinterpret_cast<float4*>(a.y_peer[p] + off), v);
   if (a.y_mc) {
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.y_mc + off), "f"(v.x), "f"(v.y),
                  "f"(v.z), "f"(v.w)
@@ -222,6 +222,48 @@ __global__ void __launch_bounds__(kThreads) gather_rows_kernel(const __grid_cons
   }
 }
 
+// Rows [ra, rb) of the local y (finished and visible to this CTA) -> peers' replicas / multicast address.
+// peer_need (halo exchange) selects per row which peers receive it.  The masks are staged in shared memory
+// first (one coalesced load), then every thread moves two independent 16-byte chunks per iteration so the
+// L2 re-reads overlap; rows nobody needs cost one shared-memory read.
+template <bool PEER>
+__device__ __forceinline__ void push_rows(const GatherArgs& a, int64_t ra, int64_t rb, int tid, int nthreads,
+                                          uint32_t* s_need) {
+  if (!PEER || a.y == nullptr || rb <= ra) return;
+  const int V = a.d >> 2;
+  const uint32_t all = (1u << a.n_peer) - 1u;
+  const int nrow = int(rb - ra);
+  const bool mc = a.y_mc != nullptr;
+  for (int j = tid; j < nrow; j += nthreads)
+    s_need[j] = mc ? 1u : ((a.peer_need ? __ldg(a.peer_need + ra + j) : 0xffffffffu) & all);
+  __syncthreads();
+  const int total = nrow * V;
+  auto send = [&](int64_t off, uint32_t need, const float4& v) {
+    if (mc) {
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.y_mc + off), "f"(v.x), "f"(v.y),
+                   "f"(v.z), "f"(v.w)
+                   : "memory");
+    } else {
+      for (int p = 0; p < a.n_peer; ++p)
+        if ((need >> p) & 1u) stg_peer_f4(reinterpret_cast<float4*>(a.y_peer[p] + off), v);
+    }
+  };
+  for (int i0 = tid; i0 < total; i0 += 2 * nthreads) {
+    const int i1 = i0 + nthreads;
+    const int j0 = i0 / V, j1 = i1 / V;
+    const uint32_t n0 = s_need[j0];
+    const uint32_t n1 = (i1 < total) ? s_need[j1] : 0u;
+    const int64_t off0 = (ra + j0) * a.ldy + int64_t(i0 - j0 * V) * 4;
+    const int64_t off1 = (ra + j1) * a.ldy + int64_t(i1 - j1 * V) * 4;
+    float4 v0 = f4_zero(), v1 = f4_zero();
+    // L2 (coherent) loads: the rows were written by this CTA a moment ago, not through the read-only path
+    if (n0) v0 = __ldcg(reinterpret_cast<const float4*>(a.y + off0));
+    if (n1) v1 = __ldcg(reinterpret_cast<const float4*>(a.y + off1));
+    if (n0) send(off0, n0, v0);
+    if (n1) send(off1, n1, v1);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // merge-path tiled kernel
 // ---------------------------------------------------------------------------
@@ -349,7 +391,7 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
         flag |= 1;
         head_pending = false;
       } else {
-        finish_row<G, CH, EPI, PEER>(a, r0 + row, acc, gl, gmask);
+        finish_row<G, CH, EPI, false>(a, r0 + row, acc, gl, gmask);
       }
 #pragma unroll
       for (int j = 0; j < CH; ++j) acc[j] = f4_zero();
@@ -504,7 +546,7 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
           for (int j = 0; j < CH; ++j)
             if (gl + G * j < V) reinterpret_cast<float4*>(ws_head)[gl + G * j] = chain[j];
         } else {
-          finish_row<G, CH, EPI, PEER>(a, r0 + row, chain, gl, gmask);
+          finish_row<G, CH, EPI, false>(a, r0 + row, chain, gl, gmask);
         }
 #pragma unroll
         for (int j = 0; j < CH; ++j) chain[j] = f4_zero();
@@ -518,6 +560,15 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
 #pragma unroll
     for (int j = 0; j < CH; ++j)
       if (gl + G * j < V) reinterpret_cast<float4*>(ws_tail)[gl + G * j] = chain[j];
+  }
+
+  // ---- fused exchange: push the rows this tile finished to the peers that gather them next ----
+  // Kept out of the gather loop on purpose: peer stores compiled into the (17x inlined) row epilogue cost
+  // 25 % of the whole launch through code size even when no row is sent.  The rows were just written to
+  // the local y by this CTA, so the re-read hits L2; chunks are contiguous per row -> 256 B NVLink writes.
+  if constexpr (PEER) {
+    __syncthreads();
+    push_rows<PEER>(a, r0 + ((rstart0 < 0) ? 1 : 0), r1, tid, kThreads, reinterpret_cast<uint32_t*>(s_rend));
   }
 }
 

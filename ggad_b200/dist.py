@@ -21,16 +21,20 @@ import torch
 import torch.distributed as dist
 
 
-def nnz_balanced_ranges(rowptr: np.ndarray, world: int) -> List[Tuple[int, int]]:
-    """Contiguous row ranges with (as near as possible) equal nnz: exact integer prefix split of rowptr.
-    Deterministic and identical on every rank."""
+def nnz_balanced_ranges(rowptr: np.ndarray, world: int, row_cost: int = 0) -> List[Tuple[int, int]]:
+    """Contiguous row ranges with (as near as possible) equal work: exact integer prefix split of
+    ``rowptr[i] + row_cost * i``.  ``row_cost = 0`` balances nnz; ``row_cost = 1`` balances the merge-path
+    items (rows + edges) of the gather kernel -- per item it moves one d-wide row (an edge gathers one, a
+    row end writes one), so this is the byte-balanced split for power-law graphs whose ranges differ a lot
+    in row count.  Deterministic and identical on every rank."""
     rowptr = np.asarray(rowptr, dtype=np.int64)
     n = len(rowptr) - 1
-    nnz = int(rowptr[-1])
+    work = rowptr + row_cost * np.arange(n + 1, dtype=np.int64) if row_cost else rowptr
+    total = int(work[-1])
     cuts = [0]
     for g in range(1, world):
-        target = (nnz * g) // world
-        r = int(np.searchsorted(rowptr, target, side="left"))
+        target = (total * g) // world
+        r = int(np.searchsorted(work, target, side="left"))
         r = min(max(r, cuts[-1]), n)
         cuts.append(r)
     cuts.append(n)

@@ -79,7 +79,6 @@ def gather_reduce(g: CSRGraph, x: torch.Tensor, *, xmap: Optional[torch.Tensor] 
             desc.peer_need = ptr(peer_need)
     if y_multicast:
         desc.y_multicast = int(y_multicast)
-        desc.y = None
     plan = g.plan
     if plan is not None:
         ws = g.workspace(d)

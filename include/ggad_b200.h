@@ -112,14 +112,14 @@ typedef struct ggad_gather_desc {
   int64_t n_tiles;
   float* ws; /* [2 * n_tiles * d] partial-row workspace */
   /* fused exchange (multi-GPU): every finished row of y is ALSO stored to these peer-mapped buffers
-   * (NVLink P2P stores from the epilogue, e.g. torch symmetric memory), or once to an NVSwitch
-   * multicast address (multimem.st).  Pointers address row 0 of THIS launch's rows inside the
+   * (NVLink P2P stores issued by the CTA that finished the row, at the end of its tile; e.g. torch
+   * symmetric memory), or once to an NVSwitch multicast address (multimem.st).  y must be given.  Pointers address row 0 of THIS launch's rows inside the
    * replicated [N, ldy] matrix of each peer; same ldy as y.  The caller synchronises the ranks
    * (barrier) before anyone reads the replicated matrix. */
   float* y_peer[7];
   int32_t n_peer;
   int32_t reserved;
-  float* y_multicast; /* NULL or multicast address covering all ranks (replaces y and y_peer) */
+  float* y_multicast; /* NULL or multicast address covering all ranks (used instead of y_peer) */
   /* halo exchange: NULL (every row goes to every peer) or [n_rows] bit masks -- bit p set means y_peer[p]
    * gathers row r in its next pass (the row is a column of that peer's CSR shard), so only those rows
    * cross NVLink.  Rows a peer does not need are left untouched in its replica. */

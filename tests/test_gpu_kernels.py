@@ -101,6 +101,33 @@ def test_gather_reduce_epilogues(use_plan, weighted):
     assert_close(r2["dot"], (y2 * x[dot_rows.long()]).sum(1) * ds, rtol=2e-4, atol=2e-3, what="dot")
 
 
+@pytest.mark.parametrize("d", [12, 64, 300])
+@pytest.mark.parametrize("epilogue", [False, True])
+def test_fused_exchange_push_single_gpu(d, epilogue):
+    """The fused exchange on ONE GPU: the "peers" are three local matrices, so the end-of-tile push phase
+    (and the fix-up kernel's peer stores for rows cut by tile boundaries) is checked bit-exactly without
+    NVLink: rows whose need bit is set equal y, all other rows stay untouched; no mask = every row."""
+    _, _, graph, ops, _ = _mods()
+    n_rows, n_cols = 6000, 5000
+    rowptr, col, val = make_csr(n_rows, n_cols, 11.0, seed=d, hub=7000, weighted=epilogue)
+    g = graph.CSRGraph.from_arrays(rowptr, col, val, n_rows, n_cols, use_plan=True)
+    x = torch.randn(n_cols, d).cuda()
+    rng = np.random.default_rng(1)
+    need = torch.from_numpy(rng.integers(0, 8, n_rows).astype(np.int32)).cuda()
+    kw = dict(bias=torch.randn(d).cuda(), relu=True, want_sumsq=True) if epilogue else {}
+    y_ref = ops.gather_reduce(g, x, **kw)["y"]
+    peers = [torch.full((n_rows, d), float("nan"), device="cuda") for _ in range(3)]
+    y = ops.gather_reduce(g, x, y_peers=[p.data_ptr() for p in peers], peer_need=need, **kw)["y"]
+    assert torch.equal(y, y_ref)
+    for s_, p in enumerate(peers):
+        sel = ((need >> s_) & 1).bool()
+        assert torch.equal(p[sel], y_ref[sel]), f"peer {s_}: needed rows differ"
+        assert bool(torch.isnan(p[~sel]).all()), f"peer {s_}: rows nobody asked for were written"
+    full = [torch.full((n_rows, d), float("nan"), device="cuda") for _ in range(2)]
+    ops.gather_reduce(g, x, y_peers=[p.data_ptr() for p in full], **kw)
+    assert all(torch.equal(p, y_ref) for p in full)
+
+
 @pytest.mark.parametrize("use_plan", [False, True])
 def test_gather_reduce_xmap(use_plan):
     _, _, graph, ops, _ = _mods()

@@ -31,7 +31,7 @@ def _worker(rank, world, port, q):
     dist.all_reduce(cnt)
     rowptr_t = np.zeros(n_glob + 1, np.int64)
     np.cumsum(cnt.cpu().numpy(), out=rowptr_t[1:])
-    br = gdist.nnz_balanced_ranges(rowptr_t, world)
+    br = gdist.nnz_balanced_ranges(rowptr_t, world, row_cost=1)
     rs_all = torch.empty(n_glob, dtype=torch.float32, device=dev)
     dist.all_gather_into_tensor(rs_all, fwd.row_scale)
     lo, hi = br[rank]

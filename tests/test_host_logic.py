@@ -68,6 +68,10 @@ def test_nnz_balanced_ranges():
         nnz = [rowptr[hi] - rowptr[lo] for lo, hi in r]
         assert sum(nnz) == rowptr[-1]
         assert max(nnz) - min(nnz) <= 2 * deg.max()
+        ri = nnz_balanced_ranges(rowptr, world, row_cost=1)                    # merge-path items (rows + edges)
+        assert ri[0][0] == 0 and ri[-1][1] == 10000 and all(ri[i][1] == ri[i + 1][0] for i in range(world - 1))
+        items = [rowptr[hi] - rowptr[lo] + hi - lo for lo, hi in ri]
+        assert sum(items) == rowptr[-1] + 10000 and max(items) - min(items) <= 2 * (deg.max() + 1)
     assert even_ranges(10, 4) == [(0, 3), (3, 6), (6, 8), (8, 10)]
     assert nnz_balanced_ranges(np.zeros(6, np.int64), 3)[-1][1] == 5          # empty graph still partitions
 

@@ -50,6 +50,13 @@ res["weighted + sumsq"] = timeit(lambda: ops.gather_reduce(gw, x, want_sumsq=Tru
 res["general (col_scale)"] = timeit(lambda: ops.gather_reduce(gw, x, col_scale=cs, use_graph_scales=False))
 res["general, 1/7 of columns non-zero (affinity backward)"] = timeit(
     lambda: ops.gather_reduce(gw, x, col_scale=torch.zeros(n, device="cuda").index_fill_(0, sub.long(), 1.0), use_graph_scales=False))
+# fused-exchange variant on one GPU: the "peer" is a local matrix, so only the kernel-side cost of the push phase shows
+peer = torch.empty(n, d, device="cuda")
+zero = torch.zeros(n, dtype=torch.int32, device="cuda")
+some = (torch.rand(n, device="cuda") < 0.42).to(torch.int32)
+res["push variant, no row needed"] = timeit(lambda: ops.gather_reduce(g, x, y_peers=[peer.data_ptr()], peer_need=zero))
+res["push variant, 42 % of rows to one local peer"] = timeit(lambda: ops.gather_reduce(g, x, y_peers=[peer.data_ptr()], peer_need=some))
+res["push variant, every row to one local peer"] = timeit(lambda: ops.gather_reduce(g, x, y_peers=[peer.data_ptr()]))
 print(f"workload {a.workload}: n={n} nnz={m} d={d}")
 for k, v in res.items():
     print(f"  {k:55s} {v:8.3f} ms   {m / v / 1e6:8.2f} G edges/s")
