@@ -98,28 +98,88 @@ def cpu_reference_leg(n: int, m: int, d: int, steps: int, warmup: int):
 
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason sampler running during the timed region."""
+    """SM clock / throttle-reason sampler running DURING the timed region: NVML polled from a thread every
+    few ms (the region of a 20-step run is ~100 ms, too short for `nvidia-smi -lms`); falls back to an
+    nvidia-smi subprocess if NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index: int, period_s: float = 0.004):
+        self.index, self.period = index, period_s
+        self.proc, self.lines, self.samples, self.th = None, [], [], None
+        self.stop_flag = threading.Event()
+        self.nvml = None
+        self.t_begin, self.t_end = 0.0, float("inf")
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.index])
+            except (ValueError, IndexError):
+                pass
+        return self.index
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self._physical_index()), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((mhz, rs, time.perf_counter()))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.th.join(2)
+            nv = self.nvml
+            names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "hw_power_brake_slowdown": nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown,
+                     "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            inside = [x for x in self.samples if self.t_begin <= x[2] <= self.t_end] or self.samples
+            sm = [x[0] for x in inside]
+            reasons = sorted(k for k, bit in names.items() if any(x[1] & bit for x in inside))
+            return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=self.max_mhz, reasons=reasons,
+                        samples=len(sm), source="nvml")
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         time.sleep(0.15)
@@ -139,7 +199,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), source="nvidia-smi")
 
 
 def hbm_peak():
@@ -281,6 +341,7 @@ def native(args):
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
     launches0 = _lib.launch_count()
     barrier()
+    sampler.mark_begin()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
@@ -290,6 +351,7 @@ def native(args):
         evs[i][4].record()
     t1.record()
     barrier()
+    sampler.mark_end()
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     total_ms = t0.elapsed_time(t1)
@@ -337,7 +399,7 @@ def native(args):
     # ---- end-to-end: host buffers through the public entry points ----
     e2e = None
     if not args.no_e2e:
-        e2e = e2e_leg(args, world, rank, dev, fwd, bwd, fr, br, value)
+        e2e = e2e_leg(args, world, rank, dev, fwd, bwd, fr, br, value, rep if exchange == "halo" else None, need)
 
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
@@ -367,7 +429,7 @@ def native(args):
         dist.destroy_process_group()
 
 
-def e2e_leg(args, world, rank, dev, fwd, bwd, fr, br, value):
+def e2e_leg(args, world, rank, dev, fwd, bwd, fr, br, value, rep=None, need_y=None):
     """Same pass with host-resident features: H2D of the rank's feature shard, D2H of its dX shard + loss."""
     import ctypes as C
     import torch.distributed as dist
@@ -379,8 +441,8 @@ def e2e_leg(args, world, rank, dev, fwd, bwd, fr, br, value):
     steps = max(2, min(args.steps, 10))
     lo_b, hi_b = br[rank]
     x_host = torch.randn(n_local, d).pin_memory()
-    dx_host = torch.empty(hi_b - lo_b, d).pin_memory()
-    h2d, d2h = x_host.numel() * 4, dx_host.numel() * 4 + 8
+    dx_host = torch.empty(hi_b - lo_b, d).pin_memory() if (world == 1 or rep is None) else None
+    h2d, d2h = x_host.numel() * 4, (hi_b - lo_b) * d * 4 + 8
     times = []
     if world == 1:
         def res(c):
@@ -419,6 +481,67 @@ def e2e_leg(args, world, rank, dev, fwd, bwd, fr, br, value):
         times = [(time.perf_counter() - t0) / steps]
         assert all(float(s["loss"][0]) > 0 for s in slots)
         api = "ggad_spmm_fwd_bwd_host_enqueue (C ABI, pinned host buffers, 2 pipelined streams)"
+    elif rep is not None:
+        # N > 1, halo exchange end to end: every step copies the rank's feature shard in from pinned host memory,
+        # pushes the rows its peers' forward shards gather (ggad_halo_push), runs the fused forward (+ halo push of
+        # Y) and the backward, and copies its dX shard + loss out.  The H2D of step i+1 runs on a second stream
+        # into a staging buffer, so it overlaps the D2H of step i (PCIe is full duplex).
+        x_rep = gdist.PeerReplica(n_glob, d, fr, rank, dev)
+        need_x = gdist.halo_need_mask(fwd.col, fr, rank)
+        cur = torch.cuda.current_stream(dev)
+        h_stream = torch.cuda.Stream(device=dev)
+        stage = [torch.empty(n_local, d, device=dev) for _ in range(2)]
+        # dX leaves through the node's owner: the backward ranges are compute-balanced (rank 0 owns few hub rows,
+        # the last rank most of the graph), so the shards are re-sharded to the even node ranges over NVLink first
+        # and every rank copies out exactly n_local rows
+        dx_own = gdist.PeerBlock(n_local, d, dev)
+        dx_pin = [torch.empty(n_local, d).pin_memory() for _ in range(2)]
+        d2h = n_local * d * 4 + 4
+        loss_pin = [torch.zeros(1).pin_memory() for _ in range(2)]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+
+        def prefetch(i):
+            with torch.cuda.stream(h_stream):
+                if i >= 2:
+                    h_stream.wait_event(ev_free[i % 2])
+                stage[i % 2].copy_(x_host, non_blocking=True)
+                ev_in[i % 2].record(h_stream)
+
+        def run(i):
+            cur.wait_event(ev_in[i % 2])
+            x_rep.local_rows.copy_(stage[i % 2])
+            ev_free[i % 2].record(cur)
+            x_rep.barrier(0)                    # every rank is done gathering the previous X
+            ops.halo_push(x_rep.local_rows, x_rep.peer_row_ptrs, need_x)
+            x_rep.barrier(1)                    # all X halos have landed (and every rank finished its last backward)
+            r = ops.gather_reduce(fwd, x_rep.buf, y_out=rep.local_rows, y_peers=rep.peer_row_ptrs, peer_need=need_y,
+                                  want_sumsq=True)
+            rep.barrier(1)                      # all Y halos have landed
+            dx = ops.gather_reduce(bwd, rep.buf)["y"]
+            dx_own.barrier(0)                   # the owners' previous dX blocks have been copied out
+            gdist.reshard_rows(dx, (lo_b, hi_b), fr, dx_own)
+            dx_own.barrier(1)
+            dx_pin[i % 2].copy_(dx_own.buf, non_blocking=True)
+            loss_pin[i % 2].copy_(r["sumsq"].sum().mul_(0.5).reshape(1), non_blocking=True)
+
+        warm = 2
+        prefetch(0)
+        for i in range(warm):
+            prefetch(i + 1)
+            run(i)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(warm, warm + steps):
+            if i + 1 < warm + steps:
+                prefetch(i + 1)
+            run(i)
+        torch.cuda.synchronize()
+        times = [(time.perf_counter() - t0) / steps]
+        assert all(float(l[0]) > 0 for l in loss_pin)
+        api = ("ggad_b200.ops.halo_push + gather_reduce (fused halo exchange), pinned host shards in/out, "
+               "H2D of step i+1 overlapped with D2H of step i")
     else:
         x_full = torch.empty(n_glob, d, device=dev)
         y_full = torch.empty(n_glob, d, device=dev)

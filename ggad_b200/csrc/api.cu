@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -18,6 +19,35 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static cudaMemPool_t g_pools[64] = {};
+static std::mutex g_pool_mu;
+
+cudaError_t temp_alloc(void** p, size_t bytes, cudaStream_t st) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 64) return cudaMallocAsync(p, bytes, st);
+  cudaMemPool_t pool;
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (!g_pools[dev]) {
+      cudaMemPoolProps props = {};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      e = cudaMemPoolCreate(&g_pools[dev], &props);
+      if (e != cudaSuccess) {
+        g_pools[dev] = nullptr;
+        return e;
+      }
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(g_pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    pool = g_pools[dev];
+  }
+  return cudaMallocFromPoolAsync(p, bytes ? bytes : 8, pool, st);
+}
 
 int sm_count_cached() {
   static int cached[64];
@@ -49,6 +79,8 @@ int row_inv_norm_impl(const float*, int64_t, int64_t, int32_t, float*, float*, c
 int normalize_backward_impl(const float*, int64_t, const float*, float*, int64_t, int64_t, int32_t, cudaStream_t);
 int rmat_keys_impl(uint64_t*, int64_t, int64_t, int32_t, int32_t, uint64_t, float, float, float, int64_t, int64_t, int64_t*,
                    cudaStream_t);
+
+int halo_push_impl(const float*, int64_t, int64_t, int32_t, const uint32_t*, float* const*, int32_t, cudaStream_t);
 
 int block_rowptr_impl(const int64_t*, const int32_t*, int64_t, const int32_t*, int64_t, int, int64_t*, int64_t*, cudaStream_t);
 int block_fill_impl(const int64_t*, const int32_t*, int64_t, const int32_t*, int64_t, int, const int64_t*, int32_t*,
@@ -149,6 +181,22 @@ GGAD_API int ggad_plan_build(const int64_t* rowptr, int64_t n_rows, int64_t nnz,
 
 GGAD_API int ggad_gather_reduce(const ggad_gather_desc_t* desc, ggad_stream_t stream) {
   return gather_reduce_impl(desc, (cudaStream_t)stream);
+}
+
+GGAD_API int ggad_trim_workspace(void) {
+  int dev = 0;
+  GGAD_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (dev < 64 && g_pools[dev]) {
+    GGAD_CUDA_OK(cudaDeviceSynchronize());
+    GGAD_CUDA_OK(cudaMemPoolTrimTo(g_pools[dev], 0));
+  }
+  return GGAD_OK;
+}
+
+GGAD_API int ggad_halo_push(const float* y, int64_t ldy, int64_t n_rows, int32_t d, const uint32_t* peer_need,
+                            float* const* y_peer_host, int32_t n_peer, ggad_stream_t stream) {
+  return halo_push_impl(y, ldy, n_rows, d, peer_need, y_peer_host, n_peer, (cudaStream_t)stream);
 }
 
 GGAD_API int ggad_normalize_backward(const float* e, int64_t lde, const float* inv_norm, float* g, int64_t ldg, int64_t n_rows,

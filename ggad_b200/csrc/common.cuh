@@ -29,6 +29,11 @@ void count_launch(int n = 1);
     }                                  \
   } while (0)
 
+// Stream-ordered temporary from the library's own memory pool (api.cu).  The pool keeps what it has allocated
+// across synchronisations (release threshold = max), so a per-batch caller (the mini-batch frontier) does not pay
+// the driver for physical memory on every call; ggad_trim_workspace() gives it back.  Free with cudaFreeAsync.
+cudaError_t temp_alloc(void** p, size_t bytes, cudaStream_t st);
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---------------------------------------------------------------------------

@@ -269,13 +269,13 @@ int coo_keys_to_csr_impl(uint64_t* keys, int64_t n, int64_t n_rows, int64_t* row
   GGAD_REQUIRE(n >= 0 && n_rows >= 0 && rowptr && (n == 0 || (keys && col)), GGAD_ERR_INVALID, "coo_keys_to_csr: bad arguments");
   if (n > 0) {
     uint64_t* alt = nullptr;
-    GGAD_CUDA_OK(cudaMallocAsync(&alt, size_t(n) * 8, st));
+    GGAD_CUDA_OK(temp_alloc(reinterpret_cast<void**>(&alt), size_t(n) * 8, st));
     cub::DoubleBuffer<uint64_t> db(keys, alt);
     size_t tmp_bytes = 0;
     const int end_bit = 32 + bits_for(n_rows);
     GGAD_CUDA_OK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, db, n, 0, end_bit, st));
     void* tmp = nullptr;
-    GGAD_CUDA_OK(cudaMallocAsync(&tmp, tmp_bytes, st));
+    GGAD_CUDA_OK(temp_alloc(reinterpret_cast<void**>(&tmp), tmp_bytes, st));
     GGAD_CUDA_OK(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, db, n, 0, end_bit, st));
     if (db.Current() != keys) GGAD_CUDA_OK(cudaMemcpyAsync(keys, db.Current(), size_t(n) * 8, cudaMemcpyDeviceToDevice, st));
     GGAD_CUDA_OK(cudaFreeAsync(tmp, st));
@@ -299,11 +299,11 @@ int csr_transpose_impl(const int64_t* rowptr, const int32_t* col, const float* v
   int64_t *i0 = nullptr, *i1 = nullptr;
   const bool need_idx = (val != nullptr) || (perm != nullptr);
   if (nnz > 0) {
-    GGAD_CUDA_OK(cudaMallocAsync(&k0, size_t(nnz) * 8, st));
-    GGAD_CUDA_OK(cudaMallocAsync(&k1, size_t(nnz) * 8, st));
+    GGAD_CUDA_OK(temp_alloc(reinterpret_cast<void**>(&k0), size_t(nnz) * 8, st));
+    GGAD_CUDA_OK(temp_alloc(reinterpret_cast<void**>(&k1), size_t(nnz) * 8, st));
     if (need_idx) {
-      GGAD_CUDA_OK(cudaMallocAsync(&i0, size_t(nnz) * 8, st));
-      GGAD_CUDA_OK(cudaMallocAsync(&i1, size_t(nnz) * 8, st));
+      GGAD_CUDA_OK(temp_alloc(reinterpret_cast<void**>(&i0), size_t(nnz) * 8, st));
+      GGAD_CUDA_OK(temp_alloc(reinterpret_cast<void**>(&i1), size_t(nnz) * 8, st));
     }
     transpose_keys<<<blocks_for(nnz), 256, 0, st>>>(rowptr, col, n_rows, nnz, k0, i0);
     GGAD_CUDA_OK(cudaGetLastError());
@@ -317,7 +317,7 @@ int csr_transpose_impl(const int64_t* rowptr, const int32_t* col, const float* v
     if (need_idx) {
       cub::DoubleBuffer<int64_t> di(i0, i1);
       GGAD_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, di, nnz, 0, end_bit, st));
-      GGAD_CUDA_OK(cudaMallocAsync(&tmp, tmp_bytes, st));
+      GGAD_CUDA_OK(temp_alloc(reinterpret_cast<void**>(&tmp), tmp_bytes, st));
       GGAD_CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, di, nnz, 0, end_bit, st));
       if (val) {
         gather_vals<<<blocks_for(nnz), 256, 0, st>>>(val, di.Current(), nnz, valT);
@@ -327,7 +327,7 @@ int csr_transpose_impl(const int64_t* rowptr, const int32_t* col, const float* v
       if (perm) GGAD_CUDA_OK(cudaMemcpyAsync(perm, di.Current(), size_t(nnz) * 8, cudaMemcpyDeviceToDevice, st));
     } else {
       GGAD_CUDA_OK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, dk, nnz, 0, end_bit, st));
-      GGAD_CUDA_OK(cudaMallocAsync(&tmp, tmp_bytes, st));
+      GGAD_CUDA_OK(temp_alloc(reinterpret_cast<void**>(&tmp), tmp_bytes, st));
       GGAD_CUDA_OK(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, dk, nnz, 0, end_bit, st));
     }
     low32_of_keys<<<blocks_for(nnz), 256, 0, st>>>(dk.Current(), nnz, colT);
@@ -377,13 +377,13 @@ int block_rowptr_impl(const int64_t* rowptr, const int32_t* col, int64_t n_nodes
   GGAD_REQUIRE(rowptr && (nodes || n_batch == 0) && block_rowptr && nnz_host && n_batch >= 0 && n_nodes >= 0,
                GGAD_ERR_INVALID, "block_rowptr: bad arguments");
   int64_t* deg = nullptr;
-  GGAD_CUDA_OK(cudaMallocAsync(&deg, size_t(n_batch + 1) * 8, st));
+  GGAD_CUDA_OK(temp_alloc(reinterpret_cast<void**>(&deg), size_t(n_batch + 1) * 8, st));
   block_degree_kernel<<<blocks_for(n_batch + 1), 256, 0, st>>>(rowptr, col, n_nodes, nodes, n_batch, add_self, deg);
   GGAD_CUDA_OK(cudaGetLastError());
   size_t tmp_bytes = 0;
   GGAD_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, deg, block_rowptr, n_batch + 1, st));
   void* tmp = nullptr;
-  GGAD_CUDA_OK(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 8, st));
+  GGAD_CUDA_OK(temp_alloc(reinterpret_cast<void**>(&tmp), tmp_bytes ? tmp_bytes : 8, st));
   GGAD_CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, deg, block_rowptr, n_batch + 1, st));
   count_launch(2);
   GGAD_CUDA_OK(cudaMemcpyAsync(nnz_host, block_rowptr + n_batch, 8, cudaMemcpyDeviceToHost, st));
@@ -413,9 +413,9 @@ int unique_sorted_impl(const int32_t* keys, int64_t n, int64_t key_bound, int32_
   }
   uint32_t *k0 = nullptr, *k1 = nullptr;
   int64_t* d_count = nullptr;
-  GGAD_CUDA_OK(cudaMallocAsync(&k0, size_t(n) * 4, st));
-  GGAD_CUDA_OK(cudaMallocAsync(&k1, size_t(n) * 4, st));
-  GGAD_CUDA_OK(cudaMallocAsync(&d_count, 8, st));
+  GGAD_CUDA_OK(temp_alloc(reinterpret_cast<void**>(&k0), size_t(n) * 4, st));
+  GGAD_CUDA_OK(temp_alloc(reinterpret_cast<void**>(&k1), size_t(n) * 4, st));
+  GGAD_CUDA_OK(temp_alloc(reinterpret_cast<void**>(&d_count), 8, st));
   GGAD_CUDA_OK(cudaMemcpyAsync(k0, keys, size_t(n) * 4, cudaMemcpyDeviceToDevice, st));
   cub::DoubleBuffer<uint32_t> db(k0, k1);
   size_t sort_bytes = 0, sel_bytes = 0;
@@ -424,7 +424,7 @@ int unique_sorted_impl(const int32_t* keys, int64_t n, int64_t key_bound, int32_
   GGAD_CUDA_OK(cub::DeviceSelect::Unique(nullptr, sel_bytes, k0, reinterpret_cast<uint32_t*>(uniq), d_count, n, st));
   void* tmp = nullptr;
   const size_t tmp_bytes = sort_bytes > sel_bytes ? sort_bytes : sel_bytes;
-  GGAD_CUDA_OK(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 8, st));
+  GGAD_CUDA_OK(temp_alloc(reinterpret_cast<void**>(&tmp), tmp_bytes ? tmp_bytes : 8, st));
   size_t b = sort_bytes;
   GGAD_CUDA_OK(cub::DeviceRadixSort::SortKeys(tmp, b, db, n, 0, end_bit, st));
   b = sel_bytes;
@@ -495,7 +495,7 @@ int rmat_keys_impl(uint64_t* keys, int64_t n_edges, int64_t n_local, int32_t n_s
   unsigned long long* counter = nullptr;
   if (filtered) {
     GGAD_REQUIRE(n_out_host, GGAD_ERR_INVALID, "rmat_keys: n_out_host required with a filter");
-    GGAD_CUDA_OK(cudaMallocAsync(&counter, 8, st));
+    GGAD_CUDA_OK(temp_alloc(reinterpret_cast<void**>(&counter), 8, st));
     GGAD_CUDA_OK(cudaMemsetAsync(counter, 0, 8, st));
   }
   if (n_edges > 0) {

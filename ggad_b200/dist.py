@@ -150,6 +150,36 @@ class PeerReplica:
         self.hdl.barrier(channel=channel)
 
 
+class PeerBlock:
+    """A per-rank [n_rows, d] fp32 block in CUDA symmetric memory that peers can write into with plain copies
+    (``view(p)`` is a tensor aliasing rank p's block over NVLink).  Used to hand rows back to their owner, e.g.
+    re-sharding the backward's dX from the compute-balanced source ranges to the owners' node ranges before it
+    leaves the GPU."""
+
+    def __init__(self, n_rows: int, d: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.shape = (n_rows, d)
+        self.buf = symm.empty(self.shape, dtype=torch.float32, device=device)
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+
+    def view(self, rank: int) -> torch.Tensor:
+        return self.hdl.get_buffer(rank, self.shape, torch.float32)
+
+    def barrier(self, channel: int = 0) -> None:
+        self.hdl.barrier(channel=channel)
+
+
+def reshard_rows(local: torch.Tensor, src_range: Tuple[int, int], dst_ranges: Sequence[Tuple[int, int]],
+                 block: "PeerBlock") -> None:
+    """Copy this rank's rows [src_range) of a global row space into the owners' PeerBlocks (owner p holds
+    rows dst_ranges[p]); one NVLink memcpy per overlapping owner.  Callers barrier before reading."""
+    lo, hi = src_range
+    for p, (a, b) in enumerate(dst_ranges):
+        s, e = max(lo, a), min(hi, b)
+        if s < e:
+            block.view(p)[s - a:e - a].copy_(local[s - lo:e - lo], non_blocking=True)
+
+
 class ShardedLayerPass:
     """Forward + backward of one aggregation layer on a node-range-sharded graph.
 

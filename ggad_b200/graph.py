@@ -23,6 +23,9 @@ def _pad4(n: int) -> int:
     return (n + 3) & ~3
 
 
+TRIM_AFTER_NNZ = 1 << 24   # sorts of at least this many keys release the library's temp pool afterwards
+
+
 class CSRGraph:
     """A sparse operator A [n_rows, n_cols] in CSR on one GPU.
 
@@ -130,6 +133,8 @@ class CSRGraph:
                 with torch.cuda.device(self.device):
                     check(lib().ggad_csr_transpose(ptr(self.rowptr), ptr(self.col), ptr(self.val), self.n_rows, self.n_cols,
                                                    self.nnz, ptr(rpt), ptr(ct), ptr(vt), None, stream_ptr(self.device)))
+                    if self.nnz >= TRIM_AFTER_NNZ:      # one-off multi-GB sort buffers: hand them back to the driver
+                        check(lib().ggad_trim_workspace())
                 t = CSRGraph(rpt, ct, vt, self.n_cols, self.n_rows, row_scale=self.col_scale, col_scale=self.row_scale)
                 t = t.fold_col_scale()
             t._T = self

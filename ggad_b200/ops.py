@@ -88,6 +88,25 @@ def gather_reduce(g: CSRGraph, x: torch.Tensor, *, xmap: Optional[torch.Tensor] 
     return dict(y=y, z=z, sumsq=ss, dot=dot)
 
 
+def halo_push(y: torch.Tensor, y_peers, peer_need: Optional[torch.Tensor] = None) -> None:
+    """Store the rows of ``y`` [n, d] (a rank's own block of a replicated matrix) into the peers' replicas over
+    NVLink: row r goes to ``y_peers[p]`` (peer-mapped device addresses of the same block) iff bit p of
+    ``peer_need[r]`` is set (None = every row to every peer).  Stand-alone form of the gather kernel's
+    end-of-tile push, for matrices that no gather launch produced (layer-0 features)."""
+    import ctypes as C
+    _lib.require_cuda(y, "y")
+    assert y.dtype == torch.float32 and y.dim() == 2 and y.stride(1) == 1 and y.shape[1] % 4 == 0
+    n_peer = len(y_peers)
+    if n_peer == 0 or y.shape[0] == 0:
+        return
+    if peer_need is not None:
+        assert peer_need.dtype == torch.int32 and peer_need.numel() == y.shape[0] and peer_need.is_cuda
+    arr = (C.c_void_p * n_peer)(*[int(p) for p in y_peers])
+    with torch.cuda.device(y.device):
+        check(lib().ggad_halo_push(ptr(y), y.stride(0), y.shape[0], y.shape[1], ptr(peer_need), arr, n_peer,
+                                   stream_ptr(y.device)))
+
+
 # ------------------------------------------------------------------------------------------
 class _Spmm(torch.autograd.Function):
     """y = A x  (optionally x gathered through xmap).  dx = A^T dy."""

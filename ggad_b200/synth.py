@@ -30,6 +30,8 @@ def _keys_to_csr(keys: torch.Tensor, n_keys: int, n_rows: int, n_cols: int, row_
     col = torch.empty(n_keys, dtype=torch.int32, device=device)
     with torch.cuda.device(device):
         check(lib().ggad_coo_keys_to_csr(ptr(keys), n_keys, n_rows, ptr(rowptr), ptr(col), stream_ptr(device)))
+        if n_keys >= (1 << 24):
+            check(lib().ggad_trim_workspace())
     return rowptr, col
 
 
@@ -151,4 +153,6 @@ def rmat_adjacency(n: int, n_edges: int, seed: int = 0, device="cuda"):
     col = torch.empty(m, dtype=torch.int32, device=device)
     with torch.cuda.device(device):
         check(lib().ggad_coo_keys_to_csr(ptr(both), m, n, ptr(rowptr), ptr(col), stream_ptr(device)))
+        if m >= (1 << 24):
+            check(lib().ggad_trim_workspace())
     return DeviceAdjacency(rowptr, col, n)

@@ -54,6 +54,9 @@ GGAD_API int ggad_version(void);
 GGAD_API const char* ggad_last_error(void);
 /* number of CUDA kernels this library has launched since it was loaded */
 GGAD_API int64_t ggad_launch_count(void);
+/* The K7 index kernels take their temporaries (radix-sort double buffers, scan storage) from a library-owned
+ * stream-ordered memory pool that is kept across calls; this returns it to the driver (synchronises the device). */
+GGAD_API int ggad_trim_workspace(void);
 GGAD_API int ggad_device_info(int* sm_count, int64_t* l2_bytes, int* cc_major, int* cc_minor, int64_t* hbm_bytes);
 
 /* ---- K1/K2/K3/K5: CSR neighbor gather-reduce with fused per-row epilogue -------
@@ -127,6 +130,15 @@ typedef struct ggad_gather_desc {
 } ggad_gather_desc_t;
 
 GGAD_API int ggad_gather_reduce(const ggad_gather_desc_t* desc, ggad_stream_t stream);
+
+/* Halo exchange of a row block that was not produced by a gather launch (e.g. a rank's shard of the input
+ * features): row r of y[n_rows, ldy] is stored at the same row offset of y_peer_host[p] (HOST array of n_peer
+ * peer-mapped DEVICE pointers, each addressing row 0 of this block inside the peer's replicated matrix) for
+ * every p whose bit is set in peer_need[r] (NULL = all rows to all peers).  Same masks and semantics as
+ * ggad_gather_desc_t.peer_need; the reference has no multi-GPU path -- this is the exchange
+ * step of the destination-range sharded layer pass. */
+GGAD_API int ggad_halo_push(const float* y, int64_t ldy, int64_t n_rows, int32_t d, const uint32_t* peer_need,
+                            float* const* y_peer_host, int32_t n_peer, ggad_stream_t stream);
 
 /* Merge-path plan for a CSR: n_tiles = ceil((n_rows + nnz) / GGAD_TILE_ITEMS). */
 GGAD_API int64_t ggad_plan_num_tiles(int64_t n_rows, int64_t nnz);

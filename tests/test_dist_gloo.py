@@ -76,3 +76,56 @@ def test_sharded_layer_pass_world2():
         p.join(30)
     assert all(r[1] for r in res), res
     assert res[0][2] == res[1][2] and res[0][3] == res[1][3]      # identical partition on every rank
+
+
+def _dp_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    from ggad_b200.train import DataParallelMiniBatch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class Tiny(torch.nn.Module):                      # stands in for the drop-in GCN: same .loss() contract
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(0)
+            self.w = torch.nn.Parameter(torch.randn(5, 3))
+            self.unused = torch.nn.Parameter(torch.randn(2))     # never gets a gradient
+            self.frozen = torch.nn.Parameter(torch.randn(2), requires_grad=False)
+
+        def loss(self, nodes, labels):
+            x = torch.tensor(nodes, dtype=torch.float32).reshape(-1, 5)
+            t = ((x @ self.w).sum(1) - labels.float()).pow(2).mean()
+            return t, t, t, t
+    batches = [([1., 2, 3, 4, 5, 0, 1, 0, 1, 0], torch.tensor([1, 0])), ([2., 2, 2, 2, 2, 9, 8, 7, 6, 5], torch.tensor([0, 1]))]
+    m = Tiny()
+    dp = DataParallelMiniBatch(m, torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=1e-2))
+    for _ in range(3):
+        dp.step(*batches[rank])
+    ref = Tiny()
+    opt = torch.optim.Adam([p for p in ref.parameters() if p.requires_grad], lr=1e-2)
+    for _ in range(3):
+        opt.zero_grad()
+        (sum(ref.loss(*b)[0] for b in batches) / world).backward()
+        if ref.unused.grad is None:
+            ref.unused.grad = torch.zeros_like(ref.unused)
+        opt.step()
+    ok = torch.allclose(m.w, ref.w, rtol=1e-6, atol=1e-7) and torch.equal(m.frozen, ref.frozen)
+    q.put((rank, bool(ok), m.w.detach().tolist()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_data_parallel_minibatch_world2():
+    """Gradient averaging of the data-parallel mini-batch driver == one process minimising the mean loss."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=150) for _ in procs]
+    for p in procs:
+        p.join(30)
+    assert all(r[1] for r in res), res
+    assert res[0][2] == res[1][2]                                   # replicas stay identical

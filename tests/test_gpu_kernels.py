@@ -128,6 +128,27 @@ def test_fused_exchange_push_single_gpu(d, epilogue):
     assert all(torch.equal(p, y_ref) for p in full)
 
 
+@pytest.mark.parametrize("d,ld", [(4, 4), (64, 64), (300, 304)])
+def test_halo_push_single_gpu(d, ld):
+    """Stand-alone halo push (ggad_halo_push) with local matrices as the peers: bit-exact row selection."""
+    _, _, _, ops, _ = _mods()
+    n = 10007
+    y = torch.randn(n, ld, device="cuda")[:, :d]
+    need = torch.from_numpy(np.random.default_rng(d).integers(0, 4, n).astype(np.int32)).cuda()
+    peers = [torch.full((n, ld), float("nan"), device="cuda") for _ in range(2)]
+    ops.halo_push(y, [p.data_ptr() for p in peers], need)
+    for s_, p in enumerate(peers):
+        sel = ((need >> s_) & 1).bool()
+        assert torch.equal(p[sel][:, :d], y[sel]) and bool(torch.isnan(p[~sel]).all())
+        assert bool(torch.isnan(p[:, d:]).all())                      # padding columns beyond d are not touched
+    full = torch.full((n, ld), float("nan"), device="cuda")
+    ops.halo_push(y, [full.data_ptr()])
+    assert torch.equal(full[:, :d], y)
+    ops.halo_push(y[:0], [full.data_ptr()])                           # empty block is a no-op
+    with pytest.raises(RuntimeError):
+        ops.halo_push(y, [full.data_ptr()] * 8)                       # more than 7 peers
+
+
 @pytest.mark.parametrize("use_plan", [False, True])
 def test_gather_reduce_xmap(use_plan):
     _, _, graph, ops, _ = _mods()

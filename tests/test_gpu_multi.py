@@ -74,6 +74,26 @@ def _worker(rank, world, port, q):
     halo_ok = halo_ok and torch.equal(dx_halo, dx[lo:hi])
     frac = float((need != 0).float().mean())
     rep.barrier(1)
+    # input-side halo (ggad_halo_push): each rank holds only its own block of X plus the rows its forward shard
+    # gathers, pushed by their owners; the forward on that replica is bit-identical
+    x_rep = gdist.PeerReplica(n_glob, d, fr, rank, dev)
+    need_x = gdist.halo_need_mask(fwd.col, fr, rank)
+    x_rep.buf.fill_(float("nan"))
+    x_rep.local_rows.copy_(x[fr[rank][0]:fr[rank][1]])
+    x_rep.barrier(0)
+    ops.halo_push(x_rep.local_rows, x_rep.peer_row_ptrs, need_x)
+    x_rep.barrier(1)
+    y_from_halo = ops.gather_reduce(fwd, x_rep.buf)["y"]
+    halo_ok = halo_ok and torch.equal(y_from_halo, y[fr[rank][0]:fr[rank][1]])
+    x_rep.barrier(0)
+    # hand the backward's dX rows (compute-balanced source ranges) back to the owners of the even node ranges
+    own = gdist.PeerBlock(n_local, d, dev)
+    own.buf.fill_(float("nan"))
+    own.barrier(0)
+    gdist.reshard_rows(dx_halo, br[rank], fr, own)
+    torch.cuda.synchronize()
+    own.barrier(1)
+    halo_ok = halo_ok and torch.equal(own.buf, dx[fr[rank][0]:fr[rank][1]])
     ok = fused_ok and mc_ok and halo_ok
     msg = f"fused={fused_ok} multicast={'n/a' if not rep.multicast_ptr else mc_ok} halo={halo_ok} (rows sent {frac:.2f}) "
     if rank == 0:
@@ -114,3 +134,74 @@ def test_sharded_layer_pass_nccl():
         p.join(60)
     assert all(r[1] for r in res), res
     assert all(r[3] == res[0][3] for r in res)
+
+
+def _dp_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import copy
+    import torch.distributed as dist
+    from ggad_b200 import graphsage as gs, synth
+    from ggad_b200.train import DataParallelMiniBatch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    n, d, h, B = 20000, 17, 32, 40
+    adj = synth.rmat_adjacency(n, 150000, seed=3, device=dev)
+    rng = np.random.default_rng(3)
+    feats = torch.nn.Embedding(n, d)
+    feats.weight = torch.nn.Parameter(torch.from_numpy(rng.random((n, d), dtype=np.float32)), requires_grad=False)
+    feats = feats.to(dev)
+    deg = (adj.rowptr[1:] - adj.rowptr[:-1]).cpu().numpy()
+    cand = np.flatnonzero(deg > 0)
+    batches = [[rng.choice(cand, B, replace=False).tolist() for _ in range(world)] for _ in range(3)]
+    labels = torch.cat([torch.zeros(B - 10, dtype=torch.long), torch.ones(10, dtype=torch.long)])
+
+    def make():
+        torch.manual_seed(5)
+        agg = gs.GCNAggregator(feats, cuda=True)
+        enc = gs.GCNEncoder(feats, d, h, adj, agg, gcn=True, cuda=True)
+        m = gs.GCN(2, enc).to(dev)
+        return m, torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=1e-2)
+    m, opt = make()
+    dp = DataParallelMiniBatch(m, opt)
+    for it in range(3):
+        dp.step(batches[it][rank], labels)
+    ok, msg = True, ""
+    if rank == 0:                                  # one process minimising the mean of the per-rank batch losses
+        ref, ropt = make()
+        for it in range(3):
+            ropt.zero_grad()
+            (sum(ref.loss(batches[it][r], labels)[0] for r in range(world)) / world).backward()
+            ropt.step()
+        for (k, a), (_, b) in zip(m.named_parameters(), ref.named_parameters()):
+            if a.requires_grad and not torch.allclose(a, b, rtol=1e-4, atol=1e-6):
+                ok = False
+                msg += f"{k}: max diff {float((a - b).abs().max()):.3e} "
+    w = m.weight.detach().clone()
+    lo, hi = w.clone(), w.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    ok = ok and torch.equal(lo, hi)                # replicas stay bit-identical
+    q.put((rank, bool(ok), msg))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_data_parallel_minibatch_nccl():
+    """Program B's batch, data parallel over 2 GPUs == one process on the mean of the two batch losses."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30700 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=500) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert all(r[1] for r in res), res

@@ -3,6 +3,11 @@
 (src/model_handler.py:330-364) with the drop-in modules, frontier built on the device.
 
     python tools/bench_minibatch.py [--nodes 3700550 --edges 36552754 --batch 150 --seeds 50] [--cpu-nodes 300000]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/bench_minibatch.py   (data parallel)
+
+With N ranks the graph, the feature table and the parameters are replicated, every rank draws its own seed batches
+and the parameter gradients are averaged with one all-reduce per batch (train.DataParallelMiniBatch): weak scaling,
+`batches_per_s` is the aggregate over all ranks.
 
 Also times the CPU restatement of the reference's batch (oracle, sparse; the reference's own dense-mask batch
 took 1.52 s on a 300 k-node proxy in the survey) on a smaller graph of the same generator.  One JSON line.
@@ -30,9 +35,17 @@ def main():
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--cpu-nodes", type=int, default=300_000)
     ap.add_argument("--cpu-iters", type=int, default=3)
+    ap.add_argument("--diag", action="store_true", help="also time the rank-local part of every batch (adds a sync)")
     args = ap.parse_args()
     from ggad_b200 import _lib, graphsage as gs, synth
-    dev = torch.device("cuda")
+    from ggad_b200.train import DataParallelMiniBatch
+    import torch.distributed as dist
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     adj = synth.rmat_adjacency(args.nodes, args.edges, seed=72, device=dev)
     n, d, h = args.nodes, args.d, args.h
     rng = np.random.default_rng(72)
@@ -40,11 +53,14 @@ def main():
     x = x / (x.sum(1, keepdims=True) + 0.01)                      # src/utils.py:79 normalisation
     feats = torch.nn.Embedding(n, d)
     feats.weight = torch.nn.Parameter(torch.from_numpy(x), requires_grad=False)
-    feats = feats.cuda()
+    feats = feats.to(dev)
     agg = gs.GCNAggregator(feats, cuda=True)
+    torch.manual_seed(72)                                         # identical initial parameters on every rank
     enc = gs.GCNEncoder(feats, d, h, adj, agg, gcn=True, cuda=True)
-    model = gs.GCN(2, enc).cuda()
+    model = gs.GCN(2, enc).to(dev)
     opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3, weight_decay=0.007)
+    dp = DataParallelMiniBatch(model, opt)
+    rng = np.random.default_rng(72 + 1000 * rank)                 # ... and different seed batches
     deg = (adj.rowptr[1:] - adj.rowptr[:-1]).cpu().numpy()
     cand = np.flatnonzero(deg > 0)
     B = args.batch + args.seeds
@@ -52,14 +68,27 @@ def main():
 
     def batch(i):
         nodes = rng.choice(cand, B, replace=False).tolist()
-        opt.zero_grad()
-        total, cls, margin, rec = model.loss(nodes, labels)
-        total.backward()
-        opt.step()
-        return total
+        if args.diag:
+            opt.zero_grad(set_to_none=True)
+            t0 = time.perf_counter()
+            out = model.loss(nodes, labels)
+            out[0].backward()
+            torch.cuda.synchronize()
+            local_ms.append((time.perf_counter() - t0) * 1e3)
+            dp.allreduce_grads()
+            opt.step()
+            return out[0]
+        return dp.step(nodes, labels)[0]
+
+    local_ms = []
 
     stats = []
     for i in range(args.iters + 3):
+        if i == 3:
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t_all = time.perf_counter()
         torch.cuda.synchronize()
         l0 = _lib.launch_count()
         t0 = time.perf_counter()
@@ -69,16 +98,35 @@ def main():
         hop1, hop2 = agg.last_blocks
         stats.append(((time.perf_counter() - t0) * 1e3, _lib.launch_count() - l0, hop1.n_cols,
                       int(hop1.col_d.numel()), hop2.n_cols, int(hop2.col_d.numel())))
+    wall = torch.tensor([time.perf_counter() - t_all], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(wall, op=dist.ReduceOp.MAX)
     st = np.array(stats[3:], dtype=np.float64)
     ms = float(np.median(st[:, 0]))
+    agg_bps = world * args.iters / float(wall.item())
+    w0 = model.weight.detach().clone()
+    if world > 1:                                                  # replicas must stay bit-identical
+        wmin, wmax = w0.clone(), w0.clone()
+        dist.all_reduce(wmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(wmax, op=dist.ReduceOp.MAX)
+        assert torch.equal(wmin, wmax), "data-parallel replicas diverged"
     edges = float(np.mean(st[:, 3] + st[:, 5]))
     out = {"workload": "C4 mini-batch GGAD", "nodes": n, "adjacency_entries": int(adj.col.numel()), "d": d, "h": h,
-           "batch": B, "ms_per_batch": ms, "batches_per_s": 1e3 / ms, "ggad_launches_per_batch": float(np.mean(st[:, 1])),
+           "batch": B, "n_gpus": world, "ms_per_batch": ms, "batches_per_s": agg_bps, "batches_per_s_per_gpu": agg_bps / world, "ggad_launches_per_batch": float(np.mean(st[:, 1])),
            "mean_frontier_U": float(np.mean(st[:, 2])), "mean_hop1_edges": float(np.mean(st[:, 3])),
            "mean_frontier_U2": float(np.mean(st[:, 4])), "mean_hop2_edges": float(np.mean(st[:, 5])),
-           "edges_per_s": edges / (ms * 1e-3), "loss": lv,
+           "edges_per_s": edges * agg_bps, "loss": lv,
            "reference_cpu_s_per_batch_300k_proxy_survey": 1.52}
-    if args.cpu_nodes > 0:
+    if args.diag:
+        per = {"rank": rank, "local_ms": [round(float(np.percentile(local_ms[3:], q)), 2) for q in (10, 50, 90, 100)],
+               "step_ms": [round(float(np.percentile(st[:, 0], q)), 2) for q in (10, 50, 90, 100)]}
+        allp = [None] * world
+        if world > 1:
+            dist.all_gather_object(allp, per)
+        else:
+            allp = [per]
+        out["diag_p10_p50_p90_max"] = allp
+    if args.cpu_nodes > 0 and world == 1:
         import oracle
         na = args.cpu_nodes
         adj_c = synth.rmat_adjacency(na, int(args.edges * na / n), seed=72, device=dev)
@@ -101,7 +149,11 @@ def main():
             tt.append(time.perf_counter() - t0)
         out.update({"cpu_oracle_s_per_batch": float(np.median(tt)), "cpu_graph_nodes": na, "cpu_threads": torch.get_num_threads(),
                     "cpu_dict_build_s": t_dict})
-    print(json.dumps(out))
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
