@@ -236,6 +236,9 @@ def native(args):
     abc = tuple(float(t) for t in args.rmat.split(",")) if args.rmat else None
     fwd = synth.rmat_shard(n_local, m_local, world, rank, seed=args.seed, device=dev, mean=True, abc=abc)
     fr = [(g * n_local, (g + 1) * n_local) for g in range(world)]
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    x = torch.randn(n_glob, d, device=dev, generator=gen)
+    row_cost = None
     if world == 1:
         bwd = fwd.T
         br = fr
@@ -246,20 +249,48 @@ def native(args):
         dist.all_reduce(cnt)
         rowptr_t = torch.zeros(n_glob + 1, dtype=torch.int64, device=dev)
         torch.cumsum(cnt, 0, out=rowptr_t[1:])
-        br = gdist.nnz_balanced_ranges(rowptr_t.cpu().numpy(), world, row_cost=args.row_cost)   # balance rows + edges
+        rowptr_np = rowptr_t.cpu().numpy()
         del cnt, rowptr_t
         rs_all = torch.empty(n_glob, dtype=torch.float32, device=dev)
         dist.all_gather_into_tensor(rs_all, fwd.row_scale)
-        lo, hi = br[rank]
-        bwd = synth.rmat_transposed_shard(n_local, m_local, world, args.seed, lo, hi, device=dev, col_scale=rs_all,
-                                          abc=abc).fold_col_scale()
+
+        def build_bwd(rc):
+            ranges = gdist.nnz_balanced_ranges(rowptr_np, world, row_cost=rc)     # balance edges + rc * rows
+            lo, hi = ranges[rank]
+            g = synth.rmat_transposed_shard(n_local, m_local, world, args.seed, lo, hi, device=dev, col_scale=rs_all,
+                                            abc=abc).fold_col_scale()
+            g.plan
+            return ranges, g
+
+        if args.row_cost == "auto":
+            # profile-guided split: time the backward gather on a first split, fit t = a*nnz + b*rows over the
+            # ranks (their shards differ a lot in shape: hubs vs. tail), re-split with row cost b/a
+            row_cost = 2.0
+            br, bwd = build_bwd(row_cost)
+            for _ in range(2):
+                ops.gather_reduce(bwd, x)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier()
+            e0.record()
+            for _ in range(3):
+                ops.gather_reduce(bwd, x)
+            e1.record()
+            torch.cuda.synchronize()
+            samples = [None] * world
+            dist.all_gather_object(samples, [bwd.n_rows, bwd.nnz, e0.elapsed_time(e1) / 3.0])
+            fit = gdist.fit_row_cost(samples)
+            if fit is not None and abs(fit - row_cost) > 0.15 * row_cost:
+                del bwd
+                row_cost = round(fit * 16) / 16.0
+                br, bwd = build_bwd(row_cost)
+        else:
+            row_cost = float(args.row_cost)
+            br, bwd = build_bwd(row_cost)
     for g in (fwd, bwd):
         g.plan
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build
 
-    gen = torch.Generator(device=dev).manual_seed(1234)
-    x = torch.randn(n_glob, d, device=dev, generator=gen)
     y_full = torch.empty(n_glob, d, device=dev) if (world > 1 and args.exchange == "nccl") else None
 
     def compute(g, inp):
@@ -376,12 +407,13 @@ def native(args):
     total_edges = m_local * world
     value = total_edges / (ms_per_step * 1e-3)
 
+    clk_mhz = (clocks or {}).get("sm_mhz") if rank == 0 else None
     # ---- roofline of the dominant kernel (forward gather) ----
     peak, peak_src = hbm_peak()
     b_alg = fwd.algorithmic_bytes(d)
     fwd_s = seg_mean[0] * 1e-3
     achieved = b_alg / fwd_s / 1e9
-    roofline = dict(bound="hbm", kernel="gather_tiled_kernel<16,1> (forward, + tile_fixup)", achieved=achieved, peak=peak,
+    roofline = dict(bound="hbm", kernel="gather_tiled_kernel<G=16,CH=1,MODE=0,EPI=0,PEER=%d> (forward gather, + tile_fixup)" % int(world > 1), achieved=achieved, peak=peak,
                     unit="GB/s", frac=achieved / peak, traffic=None, peak_source=peak_src,
                     algorithmic_bytes=int(b_alg), fwd_ms=float(seg_mean[0]), bwd_ms=float(seg_mean[2]),
                     fwd_edges_per_s=m_local / fwd_s,
@@ -389,10 +421,19 @@ def native(args):
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            tr = json.load(open(prof)).get(args.workload)
+            tr = json.load(open(prof)).get(args.workload) if world == 1 else None   # captured at N = 1 only
             if tr:
                 roofline["traffic"] = tr["fwd_dram_bytes"]
                 roofline["traffic_source"] = tr.get("source")
+                if tr.get("fwd_l2_to_sm_bytes"):
+                    # secondary ceiling (from the same ncu capture): on R-MAT graphs half of the gathers hit L2 and
+                    # the launch runs at the measured L2 -> SM fabric ceiling before HBM saturates
+                    cap = tr["l2_to_sm_ceiling_bytes_per_cycle"] * (clk_mhz or 1965.0) * 1e6 / 1e9
+                    roofline["l2_fabric"] = {"bytes_per_launch": tr["fwd_l2_to_sm_bytes"],
+                                             "achieved_GBs": tr["fwd_l2_to_sm_bytes"] / fwd_s / 1e9,
+                                             "ceiling_GBs": cap, "frac": tr["fwd_l2_to_sm_bytes"] / fwd_s / 1e9 / cap,
+                                             "ceiling_source": "B300_MICROARCH.md LTS cap ~6300 B/cycle x SM clock; "
+                                                               "ncu lts2xbar = %d B/cycle" % tr["fwd_l2_to_sm_bytes_per_cycle"]}
         except Exception:
             pass
 
@@ -416,7 +457,7 @@ def native(args):
                        "global_nodes": n_glob, "global_edges": total_edges, "aggregation": "mean (row_scale = 1/deg)",
                        "l2": "inputs larger than L2 (no flush)" if n_glob * d * 4 > 2e8 else "L2-resident operand (no flush)",
                        "parallelism": f"dst-node-range x{world}, exchange={exchange}", "graph_build_s": round(t_build, 2),
-                       "halo_rows_sent_frac": halo_frac, "bwd_ranges": [list(map(int, r)) for r in br],
+                       "halo_rows_sent_frac": halo_frac, "bwd_ranges": [list(map(int, r)) for r in br], "bwd_row_cost": row_cost,
                        "bwd_shard_rows_nnz": shard_stats},
             "segments_ms": {"fwd_compute": float(seg_mean[0]), "fwd_exchange": float(seg_mean[1]),
                             "bwd_compute": float(seg_mean[2]), "bwd_exchange": float(seg_mean[3]),
@@ -606,8 +647,9 @@ def main():
                     help="N>1: how the forward output reaches the ranks that gather it next.  halo = NVLink P2P stores "
                          "from the gather epilogue, only rows a peer's next pass reads; fused = same, every row to every "
                          "peer; multicast = one NVSwitch multimem.st per row; nccl = separate all-gather")
-    ap.add_argument("--row-cost", type=int, default=3,
-                    help="N>1: cost of one output row in edges when the backward ranges are balanced")
+    ap.add_argument("--row-cost", default="auto",
+                    help="N>1: cost of one output row in edges when the backward ranges are balanced; 'auto' fits it from "
+                         "a timed trial split (profile-guided)")
     ap.add_argument("--peer-debug", default=None, choices=["zero_mask", "local_peers"],
                     help="diagnostics only (results are NOT exchanged): isolate the cost of the peer stores")
     ap.add_argument("--no-e2e", action="store_true")

@@ -21,15 +21,16 @@ import torch
 import torch.distributed as dist
 
 
-def nnz_balanced_ranges(rowptr: np.ndarray, world: int, row_cost: int = 0) -> List[Tuple[int, int]]:
+def nnz_balanced_ranges(rowptr: np.ndarray, world: int, row_cost: float = 0.0) -> List[Tuple[int, int]]:
     """Contiguous row ranges with (as near as possible) equal work: exact integer prefix split of
-    ``rowptr[i] + row_cost * i``.  ``row_cost = 0`` balances nnz; ``row_cost = 1`` balances the merge-path
-    items (rows + edges) of the gather kernel -- per item it moves one d-wide row (an edge gathers one, a
-    row end writes one), so this is the byte-balanced split for power-law graphs whose ranges differ a lot
-    in row count.  Deterministic and identical on every rank."""
+    ``rowptr[i] + row_cost * i`` (row_cost is quantised to 1/16 so the arithmetic stays in int64).
+    ``row_cost = 0`` balances nnz; ``row_cost = 1`` balances the merge-path items (rows + edges) of the
+    gather kernel; larger values weight the output row (a full-width HBM write) against a gathered edge
+    (which often hits L2) -- see fit_row_cost.  Deterministic and identical on every rank."""
     rowptr = np.asarray(rowptr, dtype=np.int64)
     n = len(rowptr) - 1
-    work = rowptr + row_cost * np.arange(n + 1, dtype=np.int64) if row_cost else rowptr
+    q = int(round(float(row_cost) * 16))
+    work = rowptr * 16 + q * np.arange(n + 1, dtype=np.int64) if q else rowptr
     total = int(work[-1])
     cuts = [0]
     for g in range(1, world):
@@ -39,6 +40,20 @@ def nnz_balanced_ranges(rowptr: np.ndarray, world: int, row_cost: int = 0) -> Li
         cuts.append(r)
     cuts.append(n)
     return [(cuts[g], cuts[g + 1]) for g in range(world)]
+
+
+def fit_row_cost(stats: Sequence[Sequence[float]], lo: float = 0.5, hi: float = 8.0) -> Optional[float]:
+    """Profile-guided weight for nnz_balanced_ranges: given one (rows, nnz, seconds) sample per rank of the
+    same gather launch on differently shaped shards, least-squares fit  t = a * nnz + b * rows  and return
+    b / a (cost of one output row in edges), clipped to [lo, hi]; None if the samples do not determine it."""
+    m = np.asarray([[float(s[1]), float(s[0])] for s in stats], dtype=np.float64)
+    t = np.asarray([float(s[2]) for s in stats], dtype=np.float64)
+    if len(stats) < 2 or np.linalg.matrix_rank(m) < 2:
+        return None
+    (a, b), *_ = np.linalg.lstsq(m, t, rcond=None)
+    if not (a > 0):
+        return None
+    return float(min(max(b / a, lo), hi))
 
 
 def even_ranges(n: int, world: int) -> List[Tuple[int, int]]:

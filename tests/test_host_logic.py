@@ -76,6 +76,22 @@ def test_nnz_balanced_ranges():
     assert nnz_balanced_ranges(np.zeros(6, np.int64), 3)[-1][1] == 5          # empty graph still partitions
 
 
+def test_fit_row_cost_recovers_the_cost_model():
+    """Profile-guided split: per-rank (rows, nnz, seconds) samples -> cost of a row in edges."""
+    from ggad_b200.dist import fit_row_cost, nnz_balanced_ranges
+    a, b = 2.0e-8, 5.0e-8
+    shards = [(300_000, 142_000_000), (5_800_000, 126_000_000), (18_700_000, 87_000_000)]
+    samples = [(r, m, a * m + b * r) for r, m in shards]
+    assert abs(fit_row_cost(samples) - b / a) < 1e-6
+    assert fit_row_cost(samples[:1]) is None                               # one sample determines nothing
+    assert fit_row_cost([(10, 100, 1.0), (20, 200, 2.0)]) is None           # collinear shapes
+    assert fit_row_cost([(r, m, 1e-8 * m + 1e-6 * r) for r, m in shards]) == 8.0     # clipped
+    # fractional costs stay exact-integer splits and identical for identical inputs
+    rowptr = np.concatenate([[0], np.cumsum(np.random.default_rng(1).integers(0, 50, 1000))]).astype(np.int64)
+    r1 = nnz_balanced_ranges(rowptr, 4, row_cost=1.8125)
+    assert r1 == nnz_balanced_ranges(rowptr.copy(), 4, row_cost=1.8125) and r1[-1][1] == 1000
+
+
 def test_planted_graph_and_power_law_generators():
     from ggad_b200 import synth
     a, x, y = synth.planted_anomaly_graph(800, 10.0, 16, 0.08, seed=1)
