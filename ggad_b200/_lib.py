@@ -50,6 +50,7 @@ SIGNATURES = {
     "ggad_last_error": (C.c_char_p, []),
     "ggad_launch_count": (_i64, []),
     "ggad_trim_workspace": (C.c_int, []),
+    "ggad_reserve_workspace": (C.c_int, [_i64, _vp]),
     "ggad_device_info": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "ggad_gather_reduce": (C.c_int, [C.POINTER(GatherDesc), _vp]),
     "ggad_halo_push": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp]),

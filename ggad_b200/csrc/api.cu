@@ -194,6 +194,14 @@ GGAD_API int ggad_trim_workspace(void) {
   return GGAD_OK;
 }
 
+GGAD_API int ggad_reserve_workspace(int64_t bytes, ggad_stream_t stream) {
+  if (bytes <= 0) return GGAD_OK;
+  void* p = nullptr;
+  GGAD_CUDA_OK(temp_alloc(&p, size_t(bytes), (cudaStream_t)stream));
+  GGAD_CUDA_OK(cudaFreeAsync(p, (cudaStream_t)stream));
+  return GGAD_OK;
+}
+
 GGAD_API int ggad_halo_push(const float* y, int64_t ldy, int64_t n_rows, int32_t d, const uint32_t* peer_need,
                             float* const* y_peer_host, int32_t n_peer, ggad_stream_t stream) {
   return halo_push_impl(y, ldy, n_rows, d, peer_need, y_peer_host, n_peer, (cudaStream_t)stream);

@@ -306,6 +306,21 @@ class DeviceAdjacency:
         _lib.require_cuda(rowptr, "rowptr")
         assert rowptr.dtype == torch.int64 and col.dtype == torch.int32
         self.rowptr, self.col, self.n, self.device = rowptr.contiguous(), col.contiguous(), int(n), rowptr.device
+        self._reserved_m = 0
+        self.reserve_edges = 0      # optional hint: expected upper bound of a hop's block edges (reserved at the first batch)
+
+    def _reserve(self, m: int, st) -> None:
+        """Frontier sizes vary a lot from batch to batch (hubs).  At every new maximum, grow both memory pools ONCE
+        to twice that size -- the library's pool for the sort buffers and torch's caching allocator for the four
+        block arrays -- so that steady-state batches never reach cudaMalloc / cuMemCreate (which cost milliseconds,
+        tens of milliseconds when the memory is peer-mapped to 7 other GPUs, and stall every rank of a
+        data-parallel step)."""
+        if m <= self._reserved_m:
+            return
+        self._reserved_m = 2 * m
+        check(lib().ggad_reserve_workspace(2 * (8 * self._reserved_m + (32 << 20)), st))
+        prime = [torch.empty(self._reserved_m, dtype=torch.int32, device=self.device) for _ in range(4)]
+        del prime
 
     def block(self, nodes: torch.Tensor, add_self: bool):
         """One aggregation hop for ``nodes`` (int32 device tensor): the union frontier and the block CSR with
@@ -323,6 +338,7 @@ class DeviceAdjacency:
             check(h.ggad_block_rowptr(ptr(self.rowptr), ptr(self.col), self.n, ptr(nodes), nb, int(add_self),
                                       ptr(block_rowptr), C.addressof(nnz), st))
             m = int(nnz.value)
+            self._reserve(max(m, int(self.reserve_edges)), st)
             cols = torch.empty(max(m, 1), dtype=torch.int32, device=dev)
             check(h.ggad_block_fill(ptr(self.rowptr), ptr(self.col), self.n, ptr(nodes), nb, int(add_self),
                                     ptr(block_rowptr), ptr(cols), st))

@@ -57,6 +57,9 @@ GGAD_API int64_t ggad_launch_count(void);
 /* The K7 index kernels take their temporaries (radix-sort double buffers, scan storage) from a library-owned
  * stream-ordered memory pool that is kept across calls; this returns it to the driver (synchronises the device). */
 GGAD_API int ggad_trim_workspace(void);
+/* Grow that pool to at least `bytes` once (stream-ordered allocate + free), so that a caller whose temporaries
+ * vary from call to call (mini-batch frontiers) does not pay the driver at every new maximum. */
+GGAD_API int ggad_reserve_workspace(int64_t bytes, ggad_stream_t stream);
 GGAD_API int ggad_device_info(int* sm_count, int64_t* l2_bytes, int* cc_major, int* cc_minor, int64_t* hbm_bytes);
 
 /* ---- K1/K2/K3/K5: CSR neighbor gather-reduce with fused per-row epilogue -------

@@ -32,9 +32,14 @@ def main():
     ap.add_argument("--h", type=int, default=64)
     ap.add_argument("--batch", type=int, default=150)
     ap.add_argument("--seeds", type=int, default=50)
-    ap.add_argument("--iters", type=int, default=30)
+    ap.add_argument("--iters", type=int, default=100)
+    ap.add_argument("--warm", type=int, default=10, help="untimed batches (frontier sizes vary; the memory pools settle)")
     ap.add_argument("--cpu-nodes", type=int, default=300_000)
     ap.add_argument("--cpu-iters", type=int, default=3)
+    ap.add_argument("--reserve-edges", type=int, default=0,
+                    help="hint for DeviceAdjacency.reserve_edges: grow the memory pools once, at the first batch, for hop "
+                         "blocks of up to this many edges (a new maximum later costs a cudaMalloc, ~1.5 s when the memory is "
+                         "peer-mapped on an 8-GPU box)")
     ap.add_argument("--diag", action="store_true", help="also time the rank-local part of every batch (adds a sync)")
     args = ap.parse_args()
     from ggad_b200 import _lib, graphsage as gs, synth
@@ -47,6 +52,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     adj = synth.rmat_adjacency(args.nodes, args.edges, seed=72, device=dev)
+    adj.reserve_edges = args.reserve_edges
     n, d, h = args.nodes, args.d, args.h
     rng = np.random.default_rng(72)
     x = rng.random((n, d), dtype=np.float32)
@@ -83,8 +89,8 @@ def main():
     local_ms = []
 
     stats = []
-    for i in range(args.iters + 3):
-        if i == 3:
+    for i in range(args.iters + args.warm):
+        if i == args.warm:
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
@@ -101,7 +107,7 @@ def main():
     wall = torch.tensor([time.perf_counter() - t_all], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(wall, op=dist.ReduceOp.MAX)
-    st = np.array(stats[3:], dtype=np.float64)
+    st = np.array(stats[args.warm:], dtype=np.float64)
     ms = float(np.median(st[:, 0]))
     agg_bps = world * args.iters / float(wall.item())
     w0 = model.weight.detach().clone()
@@ -112,13 +118,14 @@ def main():
         assert torch.equal(wmin, wmax), "data-parallel replicas diverged"
     edges = float(np.mean(st[:, 3] + st[:, 5]))
     out = {"workload": "C4 mini-batch GGAD", "nodes": n, "adjacency_entries": int(adj.col.numel()), "d": d, "h": h,
-           "batch": B, "n_gpus": world, "ms_per_batch": ms, "batches_per_s": agg_bps, "batches_per_s_per_gpu": agg_bps / world, "ggad_launches_per_batch": float(np.mean(st[:, 1])),
+           "batch": B, "n_gpus": world, "ms_per_batch": ms, "batches_per_s": agg_bps, "batches_per_s_per_gpu": agg_bps / world,
+           "wall_ms_per_lockstep_batch": float(wall.item()) / args.iters * 1e3, "max_ms_per_batch_rank0": float(st[:, 0].max()), "ggad_launches_per_batch": float(np.mean(st[:, 1])),
            "mean_frontier_U": float(np.mean(st[:, 2])), "mean_hop1_edges": float(np.mean(st[:, 3])),
            "mean_frontier_U2": float(np.mean(st[:, 4])), "mean_hop2_edges": float(np.mean(st[:, 5])),
            "edges_per_s": edges * agg_bps, "loss": lv,
            "reference_cpu_s_per_batch_300k_proxy_survey": 1.52}
     if args.diag:
-        per = {"rank": rank, "local_ms": [round(float(np.percentile(local_ms[3:], q)), 2) for q in (10, 50, 90, 100)],
+        per = {"rank": rank, "local_ms": [round(float(np.percentile(local_ms[args.warm:], q)), 2) for q in (10, 50, 90, 100)],
                "step_ms": [round(float(np.percentile(st[:, 0], q)), 2) for q in (10, 50, 90, 100)]}
         allp = [None] * world
         if world > 1:
