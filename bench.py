@@ -464,7 +464,7 @@ def native(args):
                             "per_rank": seg_ranks},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -659,10 +659,33 @@ def reference(args):
         "cpu_baseline": cpu,
         "e2e": {"value": cpu["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+_RESULT_FD = None
+
+
+def _reserve_stdout():
+    """stdout carries exactly ONE line, the result JSON: anything a library prints there (NCCL's version banner, torch
+    warnings) is sent to stderr by pointing fd 1 at fd 2; emit() writes to the saved descriptor."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        os.write(1, line)
+    else:
+        os.write(_RESULT_FD, line)
 
 
 def main():
+    _reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
