@@ -264,6 +264,51 @@ __device__ __forceinline__ void push_rows(const GatherArgs& a, int64_t ra, int64
   }
 }
 
+// EXPERIMENTAL (-DGGAD_PUSH_PER_GROUP=1, off in the shipped build): every lane group pushes the rows it finished
+// on its own right after its gather loop -- no CTA-wide barrier, the tail of one group overlaps the gathers of the
+// others.  A lane re-reads exactly the chunks it stored itself (same thread, same address: program order), two rows
+// in flight.  Rows combined across groups are pushed from registers by group 0 (two epilogue copies only).
+#ifndef GGAD_PUSH_PER_GROUP
+#define GGAD_PUSH_PER_GROUP 0
+#endif
+template <int G, int CH>
+__device__ __forceinline__ void push_group_rows(const GatherArgs& a, int64_t ra, int64_t rb, int gl) {
+  if (a.y == nullptr) return;
+  const int V = a.d >> 2;
+  const uint32_t all = (1u << a.n_peer) - 1u;
+  const bool mc = a.y_mc != nullptr;
+  auto need_of = [&](int64_t r) -> uint32_t {
+    return mc ? 1u : ((a.peer_need ? __ldg(a.peer_need + r) : 0xffffffffu) & all);
+  };
+  auto send = [&](int64_t off, uint32_t need, const float4& v) {
+    if (mc) {
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.y_mc + off), "f"(v.x), "f"(v.y),
+                   "f"(v.z), "f"(v.w)
+                   : "memory");
+    } else {
+      for (int p = 0; p < a.n_peer; ++p)
+        if ((need >> p) & 1u) stg_peer_f4(reinterpret_cast<float4*>(a.y_peer[p] + off), v);
+    }
+  };
+  for (int64_t r = ra; r < rb; r += 2) {
+    const uint32_t n0 = need_of(r);
+    const uint32_t n1 = (r + 1 < rb) ? need_of(r + 1) : 0u;
+    float4 v0[CH], v1[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const int ch = gl + G * j;
+      v0[j] = (n0 && ch < V) ? __ldcg(reinterpret_cast<const float4*>(a.y + r * a.ldy) + ch) : f4_zero();
+      v1[j] = (n1 && ch < V) ? __ldcg(reinterpret_cast<const float4*>(a.y + (r + 1) * a.ldy) + ch) : f4_zero();
+    }
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const int ch = gl + G * j;
+      if (n0 && ch < V) send(r * a.ldy + int64_t(ch) * 4, n0, v0[j]);
+      if (n1 && ch < V) send((r + 1) * a.ldy + int64_t(ch) * 4, n1, v1[j]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // merge-path tiled kernel
 // ---------------------------------------------------------------------------
@@ -365,6 +410,9 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
     int row = i1;
     int cur_end = s_rend[row];
     bool head_pending = ((i1 == 0) ? rstart0 : s_rend[i1 - 1]) < j1;  // first row began before this group
+#if GGAD_PUSH_PER_GROUP
+    const bool head0 = head_pending;
+#endif
     int flag = 0;
     float4 acc[CH];
     // Byte offset of this lane's 16-byte chunk(s) inside a row.  Lanes beyond the row width (V not a
@@ -524,6 +572,9 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
       flag |= 2;
     }
     if (gl == 0) s_flag[g] = flag;
+#if GGAD_PUSH_PER_GROUP
+    if constexpr (PEER) push_group_rows<G, CH>(a, r0 + i1 + (head0 ? 1 : 0), r0 + i2, gl);
+#endif
   }
   __syncthreads();
 
@@ -546,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
           for (int j = 0; j < CH; ++j)
             if (gl + G * j < V) reinterpret_cast<float4*>(ws_head)[gl + G * j] = chain[j];
         } else {
-          finish_row<G, CH, EPI, false>(a, r0 + row, chain, gl, gmask);
+          finish_row<G, CH, EPI, (GGAD_PUSH_PER_GROUP != 0) && PEER>(a, r0 + row, chain, gl, gmask);
         }
 #pragma unroll
         for (int j = 0; j < CH; ++j) chain[j] = f4_zero();
@@ -566,10 +617,12 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
   // Kept out of the gather loop on purpose: peer stores compiled into the (17x inlined) row epilogue cost
   // 25 % of the whole launch through code size even when no row is sent.  The rows were just written to
   // the local y by this CTA, so the re-read hits L2; chunks are contiguous per row -> 256 B NVLink writes.
+#if !GGAD_PUSH_PER_GROUP
   if constexpr (PEER) {
     __syncthreads();
     push_rows<PEER>(a, r0 + ((rstart0 < 0) ? 1 : 0), r1, tid, kThreads, reinterpret_cast<uint32_t*>(s_rend));
   }
+#endif
 }
 
 // Finish rows that were cut by tile boundaries: one lane group per tile whose first row began earlier.
