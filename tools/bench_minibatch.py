@@ -36,10 +36,10 @@ def main():
     ap.add_argument("--warm", type=int, default=10, help="untimed batches (frontier sizes vary; the memory pools settle)")
     ap.add_argument("--cpu-nodes", type=int, default=300_000)
     ap.add_argument("--cpu-iters", type=int, default=3)
-    ap.add_argument("--reserve-edges", type=int, default=0,
-                    help="hint for DeviceAdjacency.reserve_edges: grow the memory pools once, at the first batch, for hop "
-                         "blocks of up to this many edges (a new maximum later costs a cudaMalloc, ~1.5 s when the memory is "
-                         "peer-mapped on an 8-GPU box)")
+    ap.add_argument("--reserve-edges", type=int, default=-1,
+                    help="hint for DeviceAdjacency.reserve_edges: grow the memory pools ONCE for hop blocks of up to this "
+                         "many edges (a new maximum later costs a cudaMalloc, ~1.5 s when the memory is peer-mapped on an "
+                         "8-GPU box).  -1 = twice the largest block of the warm-up batches, 0 = no hint")
     ap.add_argument("--diag", action="store_true", help="also time the rank-local part of every batch (adds a sync)")
     args = ap.parse_args()
     from ggad_b200 import _lib, graphsage as gs, synth
@@ -52,7 +52,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     adj = synth.rmat_adjacency(args.nodes, args.edges, seed=72, device=dev)
-    adj.reserve_edges = args.reserve_edges
+    adj.reserve_edges = max(0, args.reserve_edges)
     n, d, h = args.nodes, args.d, args.h
     rng = np.random.default_rng(72)
     x = rng.random((n, d), dtype=np.float32)
@@ -91,6 +91,11 @@ def main():
     stats = []
     for i in range(args.iters + args.warm):
         if i == args.warm:
+            if args.reserve_edges < 0 and stats:
+                # settle the memory pools before the timed region: the next block() call (one dummy node) reserves
+                # for 2x the hint, i.e. 4x the largest hop-2 block seen so far
+                adj.reserve_edges = 2 * int(max(s_[5] for s_ in stats))
+                adj.block(torch.tensor([int(cand[0])], dtype=torch.int32, device=dev), True)
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
