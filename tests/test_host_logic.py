@@ -92,6 +92,38 @@ def test_fit_row_cost_recovers_the_cost_model():
     assert r1 == nnz_balanced_ranges(rowptr.copy(), 4, row_cost=1.8125) and r1[-1][1] == 1000
 
 
+def test_reshard_rows_index_arithmetic():
+    """dist.reshard_rows: compute-balanced source ranges -> owners' even ranges, every row lands exactly once
+    (the PeerBlock is replaced by local tensors; only the overlap arithmetic is under test)."""
+    from ggad_b200.dist import even_ranges, nnz_balanced_ranges, reshard_rows
+    n, d, world = 1000, 3, 4
+    rng = np.random.default_rng(3)
+    rowptr = np.concatenate([[0], np.cumsum(rng.pareto(1.1, n).astype(np.int64) + 1)])
+    src = nnz_balanced_ranges(rowptr, world, row_cost=1.5)          # very uneven row counts
+    dst = even_ranges(n, world)
+    full = torch.arange(n * d, dtype=torch.float32).reshape(n, d)
+
+    class Block:
+        def __init__(self):
+            self.bufs = [torch.full((hi - lo, d), float("nan")) for lo, hi in dst]
+
+        def view(self, p):
+            return self.bufs[p]
+    blk = Block()
+    for r in range(world):
+        lo, hi = src[r]
+        reshard_rows(full[lo:hi], (lo, hi), dst, blk)
+    for p, (lo, hi) in enumerate(dst):
+        assert torch.equal(blk.bufs[p], full[lo:hi])
+    assert len({hi - lo for lo, hi in src}) > 1
+
+
+def test_halo_need_mask_single_rank_is_empty():
+    from ggad_b200.dist import halo_need_mask
+    m = halo_need_mask(torch.tensor([0, 3, 3, 7], dtype=torch.int32), [(0, 10)], 0)
+    assert m.dtype == torch.int32 and m.shape == (10,) and int(m.abs().sum()) == 0
+
+
 def test_planted_graph_and_power_law_generators():
     from ggad_b200 import synth
     a, x, y = synth.planted_anomaly_graph(800, 10.0, 16, 0.08, seed=1)
