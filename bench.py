@@ -79,6 +79,12 @@ def rmat_csr_numpy(n: int, m: int, seed: int):
 def cpu_reference_leg(n: int, m: int, d: int, steps: int, warmup: int):
     """The reference's CPU implementation of the op (torch.spmm CSR fwd + autograd bwd) on all host threads."""
     import oracle
+    # all the host threads the process may use (torchrun exports OMP_NUM_THREADS=1 to its workers, which would make
+    # the reference arm single-threaded at N > 1)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        pass
     rowptr, col = rmat_csr_numpy(n, m, seed=0)
     deg = np.diff(rowptr).astype(np.float32)
     val = np.repeat(np.where(deg > 0, 1.0 / np.maximum(deg, 1), 0).astype(np.float32), np.diff(rowptr))
