@@ -46,38 +46,52 @@ RMAT = (0.57, 0.19, 0.19)
 # ----------------------------------------------------------------------------------------------
 # host-side R-MAT (numpy) for the CPU legs -- same distribution as the device generator
 # ----------------------------------------------------------------------------------------------
-def rmat_csr_numpy(n: int, m: int, seed: int):
+def rmat_csr_numpy(n: int, m: int, seed: int, chunk: int = 1 << 24):
+    """R-MAT CSR on the host with the device generator's scheme (per-level quadrant draw, rejection of ids >= n for
+    up to 32 rounds, then modulo), vectorised: float32 draws, int32 bit accumulation in 16 M-edge chunks and ONE
+    int64 key sort -- the full S64 graph (125 M edges) takes ~1 min instead of the ~4 min of a lexsort."""
     rng = np.random.default_rng(seed)
     bits = max(1, int(np.ceil(np.log2(n))))
-    a, b, c = RMAT
-    dst = np.zeros(m, dtype=np.int64)
-    src = np.zeros(m, dtype=np.int64)
-    todo = np.arange(m)
-    for _ in range(32):
-        k = len(todo)
-        d_ = np.zeros(k, dtype=np.int64)
-        s_ = np.zeros(k, dtype=np.int64)
+    a, b, c = (np.float32(t) for t in RMAT)
+    t1, t2, t3 = a, np.float32(a + b), np.float32(a + b + c)
+    keys = np.empty(m, dtype=np.int64)
+
+    def draw(k):
+        d_ = np.zeros(k, dtype=np.int32)
+        s_ = np.zeros(k, dtype=np.int32)
         for _l in range(bits):
-            u = rng.random(k)
-            q = (u >= a).astype(np.int64) + (u >= a + b) + (u >= a + b + c)
-            d_ = (d_ << 1) | (q >> 1)
-            s_ = (s_ << 1) | (q & 1)
-        dst[todo], src[todo] = d_, s_
-        bad = (d_ >= n) | (s_ >= n)
-        todo = todo[bad]
-        if len(todo) == 0:
-            break
-    dst %= n
-    src %= n
-    order = np.lexsort((src, dst))
-    dst, src = dst[order], src[order]
+            u = rng.random(k, dtype=np.float32)
+            q0, q1, q2 = u >= t1, u >= t2, u >= t3          # quadrant = q0 + q1 + q2: 0 a, 1 b, 2 c, 3 d
+            np.left_shift(d_, 1, out=d_)
+            d_ |= q1                                         # destination bit = quadrant >> 1
+            np.left_shift(s_, 1, out=s_)
+            s_ |= (q0 & ~q1) | q2                            # source bit = quadrant & 1
+        return d_, s_
+
+    for lo in range(0, m, chunk):
+        k = min(chunk, m - lo)
+        dst, src = draw(k)
+        todo = np.flatnonzero((dst >= n) | (src >= n))
+        for _ in range(31):
+            if len(todo) == 0:
+                break
+            d2, s2 = draw(len(todo))
+            dst[todo], src[todo] = d2, s2
+            todo = todo[(d2 >= n) | (s2 >= n)]
+        if len(todo):
+            dst[todo] %= n
+            src[todo] %= n
+        keys[lo:lo + k] = (dst.astype(np.int64) << 32) | src
+    keys.sort()
     rowptr = np.zeros(n + 1, dtype=np.int64)
-    np.cumsum(np.bincount(dst, minlength=n), out=rowptr[1:])
-    return rowptr, src.astype(np.int32)
+    np.cumsum(np.bincount(keys >> 32, minlength=n), out=rowptr[1:])
+    return rowptr, (keys & 0xffffffff).astype(np.int32)
 
 
-def cpu_reference_leg(n: int, m: int, d: int, steps: int, warmup: int):
-    """The reference's CPU implementation of the op (torch.spmm CSR fwd + autograd bwd) on all host threads."""
+def cpu_reference_leg(n: int, m: int, d: int, steps: int, warmup: int, budget_s: float = None):
+    """The reference's CPU implementation of the op (torch.spmm on a CSR adjacency, model.py:28-29, + autograd's
+    backward) on all host threads.  The operator is built once (run.py builds its adjacency before the epoch loop);
+    a step is spmm + backward.  With ``budget_s`` the timed steps stop early once the budget is spent (>= 3 kept)."""
     import oracle
     # all the host threads the process may use (torchrun exports OMP_NUM_THREADS=1 to its workers, which would make
     # the reference arm single-threaded at N > 1)
@@ -85,21 +99,29 @@ def cpu_reference_leg(n: int, m: int, d: int, steps: int, warmup: int):
         torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     except Exception:
         pass
+    t_gen = time.perf_counter()
     rowptr, col = rmat_csr_numpy(n, m, seed=0)
-    deg = np.diff(rowptr).astype(np.float32)
-    val = np.repeat(np.where(deg > 0, 1.0 / np.maximum(deg, 1), 0).astype(np.float32), np.diff(rowptr))
+    deg = np.diff(rowptr)
+    val = np.repeat(np.where(deg > 0, 1.0 / np.maximum(deg, 1), 0).astype(np.float32), deg)
+    a = oracle.torch_spmm_cpu_operator(rowptr, col, val, n)
+    del rowptr, col, val
     x = torch.randn(n, d)
+    t_gen = time.perf_counter() - t_gen
     times = []
+    t_begin = time.perf_counter()
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        oracle.torch_spmm_cpu_baseline(rowptr, col, val, x, backward=True)
+        oracle.torch_spmm_cpu_step(a, x, backward=True)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
+        if budget_s is not None and len(times) >= min(3, steps) and time.perf_counter() - t_begin > budget_s:
+            break
     t = float(np.mean(times))
     return dict(value=m / t, unit="edges/s", cores=torch.get_num_threads(), kind="port",
                 sample=f"R-MAT N={n} nnz={m} d={d} (same generator as the GPU workload), torch.spmm CSR fwd+bwd, "
-                       f"{steps} steps of {t:.2f} s on {torch.get_num_threads()} threads / {os.cpu_count()} cpus"), t
+                       f"{len(times)} steps of {t:.2f} s on {torch.get_num_threads()} threads / {os.cpu_count()} cpus "
+                       f"(graph built once in {t_gen:.0f} s, untimed)"), t, len(times)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -216,6 +238,48 @@ def hbm_peak():
 
 
 # ----------------------------------------------------------------------------------------------
+def verify_sampled_rows(g, table: torch.Tensor, out: torch.Tensor, n_samples: int, seed: int):
+    """Parity check at the benchmark's own size: recompute ``n_samples`` rows of out = A @ table on the CPU in fp64
+    from this rank's rowptr / col (/ val, row_scale) slices -- sample = first, last and highest-degree row + uniform
+    draws -- and compare with the kernel's rows.  Bound per element: 1e-4 * |ref| + 1e-5 * sum_e |w_e x_e| (fp32
+    rounding of a long sum is relative to the magnitude of its terms).  Returns (rows checked, max error / bound)."""
+    n = g.n_rows
+    rng = np.random.default_rng(seed)
+    deg = (g.rowptr[1:] - g.rowptr[:-1])
+    pick = np.unique(np.concatenate([[0, n - 1, int(torch.argmax(deg).item())],
+                                     rng.integers(0, n, max(0, n_samples - 3))])).astype(np.int64)
+    rows = torch.from_numpy(pick).to(g.device)
+    lo, hi = g.rowptr[rows].cpu().numpy(), g.rowptr[rows + 1].cpu().numpy()
+    lens = hi - lo
+    seg = np.zeros(len(pick) + 1, dtype=np.int64)
+    np.cumsum(lens, out=seg[1:])
+    eidx = torch.from_numpy(np.repeat(lo - seg[:-1], lens) + np.arange(seg[-1], dtype=np.int64)).to(g.device)
+    cols = g.col[eidx].long()
+    w = np.ones(seg[-1]) if g.val is None else g.val[eidx].double().cpu().numpy()
+    if g.col_scale is not None:
+        w = w * g.col_scale[cols].double().cpu().numpy()
+    uniq, inv = torch.unique(cols, return_inverse=True)
+    xr = table[uniq].double().cpu().numpy()                      # only the gathered rows leave the device
+    inv = inv.cpu().numpy()
+    rs = np.ones(len(pick)) if g.row_scale is None else g.row_scale[rows].double().cpu().numpy()
+    got = out[rows].double().cpu().numpy()
+    worst = 0.0
+    step = 1 << 18                                               # edges per chunk (bounds the fp64 temporaries)
+    ref = np.zeros_like(got)
+    mag = np.zeros_like(got)
+    row_of = np.repeat(np.arange(len(pick)), lens)
+    for a in range(0, int(seg[-1]), step):
+        b = min(a + step, int(seg[-1]))
+        t = xr[inv[a:b]] * w[a:b, None]
+        np.add.at(ref, row_of[a:b], t)
+        np.add.at(mag, row_of[a:b], np.abs(t))
+    ref *= rs[:, None]
+    mag *= np.abs(rs)[:, None]
+    bound = 1e-4 * np.abs(ref) + 1e-5 * mag + 1e-30
+    worst = float(np.max(np.abs(got - ref) / bound))
+    return len(pick), worst
+
+
 def native(args):
     import torch.distributed as dist
     from ggad_b200 import _lib, dist as gdist, ops, synth
@@ -307,7 +371,7 @@ def native(args):
     exchange = args.exchange if world > 1 else "none"
     rep = None
     need, halo_frac = None, None
-    if exchange in ("halo", "fused", "multicast"):
+    if exchange in ("halo", "chase", "fused", "multicast"):
         try:
             rep = gdist.PeerReplica(n_glob, d, fr, rank, dev)
             if exchange == "multicast" and not rep.multicast_ptr:
@@ -316,7 +380,7 @@ def native(args):
             if rank == 0:
                 print(f"[bench] symmetric memory unavailable ({e}); using NCCL all-gather", file=sys.stderr)
             exchange, rep = "nccl", None
-    if exchange == "halo":
+    if exchange in ("halo", "chase"):
         # rows of this rank's Y shard that peer p's backward shard gathers (distinct columns of its A^T rows)
         need = gdist.halo_need_mask(bwd.col, fr, rank)
         sent = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -325,6 +389,7 @@ def native(args):
         dist.all_reduce(sent)
         halo_frac = float(sent.item()) / (n_glob * (world - 1))
     peer_ptrs = rep.peer_row_ptrs if rep is not None else None
+    mc_ptr = rep.multicast_row_ptr if (rep is not None and args.mc_min > 0) else None
     if args.peer_debug == "zero_mask":          # diagnostics: PEER kernel variant, nothing crosses NVLink
         need = torch.zeros(n_local, dtype=torch.int32, device=dev)
     elif args.peer_debug == "local_peers":      # diagnostics: the peer stores land in a local scratch matrix
@@ -349,6 +414,9 @@ def native(args):
             rep.barrier(0)                       # peers finished reading the previous Y
             if exchange == "multicast":
                 ops.gather_reduce(fwd, x, y_out=rep.local_rows, y_multicast=rep.multicast_row_ptr)
+            elif exchange == "chase":
+                ops.gather_reduce(fwd, x, y_out=rep.local_rows, y_peers=peer_ptrs, peer_need=need, chase=True,
+                                  chase_ctas=args.chase_ctas, y_multicast=mc_ptr, mc_min_peers=args.mc_min)
             elif exchange == "halo":
                 ops.gather_reduce(fwd, x, y_out=rep.local_rows, y_peers=peer_ptrs, peer_need=need)
             else:
@@ -413,6 +481,40 @@ def native(args):
     total_edges = m_local * world
     value = total_edges / (ms_per_step * 1e-3)
 
+    # ---- parity at the measured size: sampled rows of Y and dX against an fp64 CPU recomputation, every rank ----
+    verified = None
+    if args.verify_rows > 0:
+        yy, dx_loc = step()
+        torch.cuda.synchronize()
+        lo_f = fr[rank][0]
+        n_y, e_y = verify_sampled_rows(fwd, x, yy[lo_f:lo_f + n_local] if yy.shape[0] == n_glob else yy, args.verify_rows, 7 + rank)
+        n_dx, e_dx = verify_sampled_rows(bwd, yy, dx_loc, args.verify_rows, 11 + rank)
+        halo_checked = 0
+        if world > 1 and exchange != "nccl":
+            # the halo rows themselves: every owner publishes a common sample of its true rows, every peer that
+            # gathers one of them compares its replica bit for bit
+            col_mark = torch.zeros(n_glob, dtype=torch.bool, device=dev)
+            col_mark[bwd.col.long()] = True
+            for g_ in range(world):
+                ids = torch.from_numpy(np.random.default_rng(100 + g_).integers(fr[g_][0], fr[g_][1], 2048)).to(dev)
+                truth = yy[ids].clone()
+                dist.broadcast(truth, src=g_)
+                if g_ != rank:
+                    sel = col_mark[ids]
+                    assert torch.equal(yy[ids][sel], truth[sel]), f"rank {rank}: halo rows from rank {g_} differ"
+                    halo_checked += int(sel.sum().item())
+            del col_mark
+        stat = torch.tensor([n_y, n_dx, halo_checked, e_y, e_dx], dtype=torch.float64, device=dev)
+        if world > 1:
+            mx = stat.clone()
+            dist.all_reduce(stat)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            stat[3:] = mx[3:]
+        n_y, n_dx, halo_checked, e_y, e_dx = stat.tolist()
+        verified = {"y_rows": int(n_y), "dx_rows": int(n_dx), "halo_rows_bit_exact": int(halo_checked),
+                    "max_err_over_bound": max(e_y, e_dx), "bound": "1e-4*|ref| + 1e-5*sum|terms| (fp64 CPU recompute)"}
+        assert max(e_y, e_dx) <= 1.0, f"parity check failed at the benchmark size: {verified}"
+
     clk_mhz = (clocks or {}).get("sm_mhz") if rank == 0 else None
     # ---- roofline of the dominant kernel (forward gather) ----
     peak, peak_src = hbm_peak()
@@ -446,13 +548,13 @@ def native(args):
     # ---- end-to-end: host buffers through the public entry points ----
     e2e = None
     if not args.no_e2e:
-        e2e = e2e_leg(args, world, rank, dev, fwd, bwd, fr, br, value, rep if exchange == "halo" else None, need)
+        e2e = e2e_leg(args, world, rank, dev, fwd, bwd, fr, br, value, rep if exchange in ("halo", "chase") else None, need)
 
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cn, cm = max(1000, n_local // args.cpu_frac), max(1000, m_local // args.cpu_frac)
-        cpu, _ = cpu_reference_leg(cn, cm, d, steps=2, warmup=1)
+        cpu, _, _ = cpu_reference_leg(cn, cm, d, steps=2, warmup=1)
 
     if rank == 0:
         out = {
@@ -469,6 +571,7 @@ def native(args):
                             "bwd_compute": float(seg_mean[2]), "bwd_exchange": float(seg_mean[3]),
                             "per_rank": seg_ranks},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "verified_rows": verified,
         }
         emit(out)
     if world > 1:
@@ -649,19 +752,23 @@ def _e2e_leg(args, world, rank, dev, fwd, bwd, fr, br, value, rep=None, need_y=N
 
 
 def reference(args):
+    """Reference arm: the reference's own CPU path for the op on the SAME config as the native arm (full per-GPU
+    workload: S64 = 6.25 M nodes / 125 M edges / d = 64, ~7 s per step on 16 threads).  K is honoured up to a wall
+    budget (--ref-budget seconds of timed steps, default 150; at least 3 steps), the JSON reports the steps run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n_local, m_local, d = args.nodes, args.edges, args.width
     cn, cm = max(1000, n_local // args.cpu_frac), max(1000, m_local // args.cpu_frac)
-    cpu, t = cpu_reference_leg(cn, cm, d, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    warm = max(1, min(args.warmup, 1 if cm > 20_000_000 else 2))
+    cpu, t, done = cpu_reference_leg(cn, cm, d, steps=max(1, args.steps), warmup=warm, budget_s=args.ref_budget)
     out = {
         "impl": "reference", "metric": "edges/sec (SpMM fwd+bwd)", "value": cpu["value"], "unit": "edges/s",
-        "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": max(1, min(args.warmup, 2)), "ms_per_step": t * 1e3,
+        "n_gpus": args.gpus, "steps": done, "warmup": warm, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (R-MAT 0.57/0.19/0.19/0.05, host numpy)",
         "config": {"workload": args.workload, "nodes_per_gpu": n_local, "edges_per_gpu": m_local, "width": d,
-                   "sample": cpu["sample"]},
+                   "same_config": args.cpu_frac == 1, "steps_requested": args.steps, "sample": cpu["sample"]},
         "cpu_baseline": cpu,
         "e2e": {"value": cpu["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -703,9 +810,19 @@ def main():
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--rmat", default=None, help="a,b,c of the R-MAT generator (default 0.57,0.19,0.19); 0.25,0.25,0.25 = uniform")
-    ap.add_argument("--cpu-frac", type=int, default=8, help="CPU legs run on 1/frac of the per-GPU workload")
-    ap.add_argument("--exchange", default="halo", choices=["halo", "fused", "multicast", "nccl"],
-                    help="N>1: how the forward output reaches the ranks that gather it next.  halo = NVLink P2P stores "
+    ap.add_argument("--cpu-frac", type=int, default=None,
+                    help="CPU legs run on 1/frac of the per-GPU workload (default: 8 for the native arm's cpu_baseline "
+                         "sample, 1 = the full config for --impl reference)")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: wall budget of the timed steps (s)")
+    ap.add_argument("--chase-ctas", type=int, default=0, help="exchange=chase: CTAs of the chase kernel (0 = library default)")
+    ap.add_argument("--mc-min", type=int, default=0,
+                    help="exchange=chase: rows needed by at least this many peers go once through the NVSwitch multicast "
+                         "address instead of one unicast store per peer (0 = never)")
+    ap.add_argument("--verify-rows", type=int, default=4096, help="rows of Y and of dX recomputed on the CPU after the timed region")
+    ap.add_argument("--exchange", default="chase", choices=["chase", "halo", "fused", "multicast", "nccl"],
+                    help="N>1: how the forward output reaches the ranks that gather it next.  chase = the gather kernel "
+                         "flags finished tiles and a concurrent kernel on a few SMs stores the halo rows over NVLink; "
+                         "halo = NVLink P2P stores "
                          "from the gather epilogue, only rows a peer's next pass reads; fused = same, every row to every "
                          "peer; multicast = one NVSwitch multimem.st per row; nccl = separate all-gather")
     ap.add_argument("--row-cost", default="auto",
@@ -722,10 +839,10 @@ def main():
         args.edges = args.edges or m
         args.width = args.width or d
     if args.impl == "reference":
-        # keep the whole CPU run to a few minutes: shrink the sample as K grows (~4 s per step at 1/8 of S64)
-        args.cpu_frac *= max(1, -(-args.steps // 25))
+        args.cpu_frac = args.cpu_frac or 1
         reference(args)
     else:
+        args.cpu_frac = args.cpu_frac or 8
         native(args)
 
 

@@ -30,7 +30,18 @@ class GatherDesc(C.Structure):
         ("sumsq", _vp), ("dot_mat", _vp), ("lddot", C.c_int64), ("dot_rows", _vp), ("dot_scale", _vp),
         ("dot_out", _vp),
         ("tile_row", _vp), ("tile_edge", _vp), ("n_tiles", C.c_int64), ("ws", _vp),
-        ("y_peer", _vp * 7), ("n_peer", C.c_int32), ("reserved", C.c_int32), ("y_multicast", _vp), ("peer_need", _vp),
+        ("y_peer", _vp * 7), ("n_peer", C.c_int32), ("tile_epoch", C.c_int32), ("y_multicast", _vp), ("peer_need", _vp),
+        ("tile_done", _vp),
+    ]
+
+
+class ChaseDesc(C.Structure):
+    """Mirror of ggad_chase_desc_t."""
+    _fields_ = [
+        ("y", _vp), ("ldy", C.c_int64), ("d", C.c_int32), ("n_peer", C.c_int32), ("rowptr", _vp), ("n_rows", C.c_int64),
+        ("tile_row", _vp), ("tile_edge", _vp), ("n_tiles", C.c_int64), ("tile_done", _vp), ("tile_epoch", C.c_int32),
+        ("n_ctas", C.c_int32), ("peer_need", _vp), ("y_peer", _vp * 7), ("y_multicast", _vp),
+        ("mc_min_peers", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -54,6 +65,7 @@ SIGNATURES = {
     "ggad_device_info": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "ggad_gather_reduce": (C.c_int, [C.POINTER(GatherDesc), _vp]),
     "ggad_halo_push": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp]),
+    "ggad_halo_chase": (C.c_int, [C.POINTER(ChaseDesc), _vp]),
     "ggad_plan_num_tiles": (_i64, [_i64, _i64]),
     "ggad_plan_build": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
     "ggad_normalize_backward": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _vp]),

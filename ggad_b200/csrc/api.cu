@@ -81,6 +81,7 @@ int rmat_keys_impl(uint64_t*, int64_t, int64_t, int32_t, int32_t, uint64_t, floa
                    cudaStream_t);
 
 int halo_push_impl(const float*, int64_t, int64_t, int32_t, const uint32_t*, float* const*, int32_t, cudaStream_t);
+int halo_chase_impl(const ggad_chase_desc_t*, cudaStream_t);
 
 int block_rowptr_impl(const int64_t*, const int32_t*, int64_t, const int32_t*, int64_t, int, int64_t*, int64_t*, cudaStream_t);
 int block_fill_impl(const int64_t*, const int32_t*, int64_t, const int32_t*, int64_t, int, const int64_t*, int32_t*,
@@ -205,6 +206,10 @@ GGAD_API int ggad_reserve_workspace(int64_t bytes, ggad_stream_t stream) {
 GGAD_API int ggad_halo_push(const float* y, int64_t ldy, int64_t n_rows, int32_t d, const uint32_t* peer_need,
                             float* const* y_peer_host, int32_t n_peer, ggad_stream_t stream) {
   return halo_push_impl(y, ldy, n_rows, d, peer_need, y_peer_host, n_peer, (cudaStream_t)stream);
+}
+
+GGAD_API int ggad_halo_chase(const ggad_chase_desc_t* desc, ggad_stream_t stream) {
+  return halo_chase_impl(desc, (cudaStream_t)stream);
 }
 
 GGAD_API int ggad_normalize_backward(const float* e, int64_t lde, const float* inv_norm, float* g, int64_t ldg, int64_t n_rows,

@@ -93,6 +93,16 @@ __device__ __forceinline__ void stg_peer_f4(float4* p, const float4& v) {
 #endif
 }
 
+// release / acquire flag accesses at GPU scope (tile-done flags between the gather kernel and ggad_halo_chase)
+__device__ __forceinline__ void st_release_gpu(int32_t* p, int32_t v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int32_t ld_acquire_gpu(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ void f4_fma(float4& a, float w, const float4& x) {
   a.x = fmaf(w, x.x, a.x);

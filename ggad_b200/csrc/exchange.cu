@@ -71,4 +71,99 @@ int halo_push_impl(const float* y, int64_t ldy, int64_t n_rows, int32_t d, const
   return GGAD_OK;
 }
 
+// ---------------------------------------------------------------------------
+// chase mode: the exchange as its own persistent kernel, fed by the gather kernel's tile-done flags
+// ---------------------------------------------------------------------------
+struct ChaseArgs {
+  const float* y;
+  int64_t ldy, n_rows, n_tiles;
+  int32_t d, n_peer, epoch, mc_min;
+  const int64_t* rowptr;
+  const int32_t* tile_row;
+  const int64_t* tile_edge;
+  const int32_t* tile_done;
+  const uint32_t* need;
+  float* peer[7];
+  float* y_mc;
+};
+
+// One warp per tile (tiles w, w + W, ...): lane 0 waits for the tile's flag, then the warp streams the tile's
+// finished rows L2 -> registers -> peers, U independent 16-byte chunks per lane in flight.  Bound: NVLink egress.
+__global__ void __launch_bounds__(256, 4) halo_chase_kernel(const __grid_constant__ ChaseArgs a) {
+  constexpr int U = 4;
+  const int lane = threadIdx.x & 31;
+  const int64_t W = int64_t(gridDim.x) * (blockDim.x >> 5);
+  const int V = a.d >> 2;
+  const uint32_t all = (1u << a.n_peer) - 1u;
+  for (int64_t k = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); k < a.n_tiles; k += W) {
+    if (lane == 0) {
+      uint32_t spins = 0;
+      while (ld_acquire_gpu(a.tile_done + k) != a.epoch) {
+        __nanosleep(200);
+        if (++spins > (1u << 23)) asm volatile("trap;");  // seconds: the producer launch is missing -- fail, don't hang
+      }
+    }
+    __syncwarp();
+    const int64_t r0 = __ldg(a.tile_row + k), r1 = __ldg(a.tile_row + k + 1);
+    if (r1 <= r0) continue;
+    // a first row that began in an earlier tile is finished (and pushed) by the fix-up kernel
+    const int64_t ra = r0 + ((r0 < a.n_rows && __ldg(a.rowptr + r0) < __ldg(a.tile_edge + k)) ? 1 : 0);
+    const int total = int(r1 - ra) * V;
+    for (int i0 = lane; i0 < total; i0 += 32 * U) {
+      float4 v[U];
+      uint32_t nd[U];
+      int64_t off[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + 32 * u;
+        nd[u] = 0u;
+        if (i < total) {
+          const int j = i / V;
+          nd[u] = (a.need ? __ldg(a.need + ra + j) : 0xffffffffu) & all;
+          off[u] = (ra + j) * a.ldy + int64_t(i - j * V) * 4;
+          // L2-coherent load: written by another SM moments ago; made visible by the acquire above
+          if (nd[u]) v[u] = __ldcg(reinterpret_cast<const float4*>(a.y + off[u]));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!nd[u]) continue;
+        if (a.y_mc && __popc(nd[u]) >= a.mc_min) {
+          asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.y_mc + off[u]), "f"(v[u].x),
+                       "f"(v[u].y), "f"(v[u].z), "f"(v[u].w)
+                       : "memory");
+        } else {
+          for (int p = 0; p < a.n_peer; ++p)
+            if ((nd[u] >> p) & 1u) stg_peer_f4(reinterpret_cast<float4*>(a.peer[p] + off[u]), v[u]);
+        }
+      }
+    }
+  }
+}
+
+int halo_chase_impl(const ggad_chase_desc_t* d, cudaStream_t st) {
+  GGAD_REQUIRE(d != nullptr, GGAD_ERR_INVALID, "halo_chase: null descriptor");
+  GGAD_REQUIRE(d->n_rows >= 0 && d->n_tiles >= 0 && d->d > 0 && d->d % 4 == 0 && d->ldy % 4 == 0 && d->ldy >= d->d,
+               GGAD_ERR_INVALID, "halo_chase: bad shape");
+  GGAD_REQUIRE(d->n_peer >= 0 && d->n_peer <= 7, GGAD_ERR_INVALID, "halo_chase: n_peer must be in [0, 7]");
+  if (d->n_rows == 0 || d->n_tiles == 0 || (d->n_peer == 0 && !d->y_multicast)) return GGAD_OK;
+  GGAD_REQUIRE(d->y && d->rowptr && d->tile_row && d->tile_edge && d->tile_done, GGAD_ERR_INVALID, "halo_chase: null pointer");
+  GGAD_REQUIRE(aligned16(d->y) && aligned16(d->y_multicast), GGAD_ERR_ALIGN, "halo_chase: y / y_multicast not 16-byte aligned");
+  ChaseArgs a;
+  a.y = d->y; a.ldy = d->ldy; a.n_rows = d->n_rows; a.n_tiles = d->n_tiles; a.d = d->d; a.n_peer = d->n_peer;
+  a.epoch = d->tile_epoch; a.mc_min = d->mc_min_peers > 0 ? d->mc_min_peers : 0x7fffffff;
+  a.rowptr = d->rowptr; a.tile_row = d->tile_row; a.tile_edge = d->tile_edge; a.tile_done = d->tile_done;
+  a.need = d->peer_need; a.y_mc = d->y_multicast;
+  for (int p = 0; p < 7; ++p) {
+    a.peer[p] = p < d->n_peer ? d->y_peer[p] : nullptr;
+    GGAD_REQUIRE(p >= d->n_peer || (a.peer[p] && aligned16(a.peer[p])), GGAD_ERR_ALIGN, "halo_chase: y_peer[%d] null or unaligned", p);
+  }
+  int ctas = d->n_ctas > 0 ? d->n_ctas : 48;
+  if (int64_t(ctas) * 8 > d->n_tiles) ctas = int((d->n_tiles + 7) / 8);
+  halo_chase_kernel<<<(unsigned)ctas, 256, 0, st>>>(a);
+  GGAD_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return GGAD_OK;
+}
+
 }  // namespace ggad

@@ -53,6 +53,8 @@ struct GatherArgs {
   int n_peer;
   float* y_mc;
   const uint32_t* peer_need;
+  int32_t* tile_done;   // chase mode: tile k publishes tile_done[k] = tile_epoch instead of pushing its rows
+  int32_t tile_epoch;
 };
 
 constexpr int kThreads = 256;
@@ -620,7 +622,13 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
 #if !GGAD_PUSH_PER_GROUP
   if constexpr (PEER) {
     __syncthreads();
-    push_rows<PEER>(a, r0 + ((rstart0 < 0) ? 1 : 0), r1, tid, kThreads, reinterpret_cast<uint32_t*>(s_rend));
+    if (a.tile_done) {
+      // chase mode: the exchange runs in ggad_halo_chase on a few SMs of its own; this CTA only publishes "rows
+      // [r0 (+1), r1) are final" -- a release store ordered after every thread's y stores by the barrier above
+      if (tid == 0) st_release_gpu(a.tile_done + k, a.tile_epoch);
+    } else {
+      push_rows<PEER>(a, r0 + ((rstart0 < 0) ? 1 : 0), r1, tid, kThreads, reinterpret_cast<uint32_t*>(s_rend));
+    }
   }
 #endif
 }
@@ -660,11 +668,14 @@ __global__ void __launch_bounds__(kThreads) tile_fixup_kernel(const __grid_const
 template <int G, int CH, int MODE, bool EPI, bool PEER>
 static int launch_tiled(const GatherArgs& a, cudaStream_t st) {
   using L = TileSmem<G, CH, MODE != 0>;
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
+  // the attribute is per device (context), so the "already set" flag is too -- per instantiation and device
+  static bool attr_done[64] = {};
+  int dev = 0;
+  GGAD_CUDA_OK(cudaGetDevice(&dev));
+  if (dev >= 64 || !attr_done[dev]) {
     GGAD_CUDA_OK(cudaFuncSetAttribute(gather_tiled_kernel<G, CH, MODE, EPI, PEER>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes));
-    attr_done = true;
+    if (dev < 64) attr_done[dev] = true;
   }
   gather_tiled_kernel<G, CH, MODE, EPI, PEER><<<(unsigned)a.n_tiles, kThreads, L::kBytes, st>>>(a);
   GGAD_CUDA_OK(cudaGetLastError());
@@ -686,7 +697,7 @@ template <int G, int CH>
 int launch_variant(const GatherArgs& a, cudaStream_t st, int sm_count) {
   if (a.n_rows == 0) return GGAD_OK;
   const bool gen = a.xmap || a.col_scale;
-  const bool peer = a.n_peer > 0 || a.y_mc;
+  const bool peer = a.n_peer > 0 || a.y_mc || a.tile_done;
   if (a.tile_row) {
     const bool epi = a.bias || a.prelu_slope || a.relu || a.z || a.sumsq || a.dot_out || (!a.y && !a.y_mc);
     if (peer) return epi ? launch_mode<G, CH, true, true>(a, st) : launch_mode<G, CH, false, true>(a, st);

@@ -89,6 +89,10 @@ int gather_reduce_impl(const ggad_gather_desc_t* d, cudaStream_t st) {
   }
   a.y_mc = d->y_multicast;
   a.peer_need = d->peer_need;
+  a.tile_done = d->tile_done;
+  a.tile_epoch = d->tile_epoch;
+  GGAD_REQUIRE(!a.tile_done || (d->tile_row && d->y && !a.y_mc), GGAD_ERR_INVALID,
+               "gather_reduce: tile_done (chase mode) needs the merge-path plan and y, and excludes y_multicast");
   GGAD_REQUIRE((d->n_peer == 0 && !a.y_mc) || d->y, GGAD_ERR_INVALID, "gather_reduce: the fused exchange needs the local y");
   GGAD_REQUIRE(!a.peer_need || (d->n_peer > 0 && !a.y_mc), GGAD_ERR_INVALID,
                "gather_reduce: peer_need needs y_peer[] and excludes y_multicast");

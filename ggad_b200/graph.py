@@ -108,6 +108,15 @@ class CSRGraph:
             self._plan = (tile_row, tile_edge, n_tiles)
         return self._plan
 
+    def chase_flags(self):
+        """(tile_done int32[n_tiles], epoch) for the chase exchange: a fresh epoch per launch, so the flags are never
+        reset (the buffer starts at 0, epochs start at 1)."""
+        if self.__dict__.get("_done") is None:
+            self._done = torch.zeros(self.plan[2], dtype=torch.int32, device=self.device)
+            self._epoch = 0
+        self._epoch = self._epoch % 0x7ffffff0 + 1
+        return self._done, self._epoch
+
     def workspace(self, d: int) -> Optional[torch.Tensor]:
         if self.plan is None:
             return None

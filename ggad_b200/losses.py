@@ -21,13 +21,13 @@ def _subset(normal_idx, abnormal_idx, device):
     cache holds references, so ids cannot be recycled under it)."""
     key = (id(normal_idx), id(abnormal_idx), str(device))
     hit = _subset_cache.get(key)
-    if (hit is None or hit[0] is not normal_idx or hit[1] is not abnormal_idx
-            or hit[2] != (len(normal_idx), len(abnormal_idx))):
-        n, a = np.asarray(normal_idx, dtype=np.int64), np.asarray(abnormal_idx, dtype=np.int64)
+    n, a = np.asarray(normal_idx, dtype=np.int64), np.asarray(abnormal_idx, dtype=np.int64)
+    probe = (hash(n.tobytes()), hash(a.tobytes()))            # content key: in-place edits of the lists are seen
+    if hit is None or hit[0] is not normal_idx or hit[1] is not abnormal_idx or hit[2] != probe:
         uniq, inv = np.unique(np.concatenate([n, a]), return_inverse=True)
         val = (torch.from_numpy(uniq.astype(np.int32)).to(device),
                torch.from_numpy(inv[:len(n)]).to(device), torch.from_numpy(inv[len(n):]).to(device))
-        hit = (normal_idx, abnormal_idx, (len(normal_idx), len(abnormal_idx)), val)
+        hit = (normal_idx, abnormal_idx, probe, val)
         if len(_subset_cache) > 8:
             _subset_cache.clear()
         _subset_cache[key] = hit
@@ -41,7 +41,8 @@ def ggad_loss(emb, logits, emb_con, emb_abnormal, raw_adj, normal_label_idx, abn
     emb [1,N,h] is Model.forward's first output (after the write-back), raw_adj is R = A + I as a
     CSRGraph (or anything CSRGraph.from_any accepts)."""
     device = emb.device
-    g_r = raw_adj if isinstance(raw_adj, CSRGraph) else CSRGraph.from_any(raw_adj, device)
+    from .model import as_graph
+    g_r = as_graph(raw_adj, device)            # converted once and cached (keyed on the object and its _version)
     # BCE (run.py:165-172): labels are [0]*|normal| + [1]*|S|
     lbl = torch.cat((torch.zeros(len(normal_label_idx), device=device),
                      torch.ones(emb_con.shape[0], device=device))).unsqueeze(1).unsqueeze(0)

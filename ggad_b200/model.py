@@ -24,8 +24,10 @@ _index_cache = {}
 
 
 def _probe(idx):
-    n = len(idx)
-    return (n, idx[0], idx[n // 2], idx[-1]) if n else (0,)
+    """Content key of an index list (the same bytes CSRGraph.rows() keys on), so a list mutated in place can never
+    be served stale device indices."""
+    import numpy as np
+    return hash(np.asarray(idx, dtype=np.int64).tobytes())
 
 
 def _device_index(idx, device) -> torch.Tensor:
@@ -96,47 +98,34 @@ class GCN(nn.Module):
         return out.unsqueeze(0) if squeeze else out
 
 
-class AvgReadout(nn.Module):
-    def forward(self, seq):
-        return torch.mean(seq, 1)
+class _Readout(nn.Module):
+    """Placeholder for the reference's four parameter-free readout modules (model.py:38-74).  Model constructs one
+    and never calls it (the GGAD path has no graph-level readout); it holds no parameters, so state_dict keys and
+    the RNG stream are unaffected."""
 
+    def __init__(self, mode):
+        super().__init__()
+        self.mode = mode
 
-class MaxReadout(nn.Module):
-    def forward(self, seq):
-        return torch.max(seq, 1).values
-
-
-class MinReadout(nn.Module):
-    def forward(self, seq):
-        return torch.min(seq, 1).values
-
-
-class WSReadout(nn.Module):
-    def forward(self, seq, query):
-        sim = F.softmax(torch.matmul(seq, query.permute(0, 2, 1)), dim=1).repeat(1, 1, 64)
-        return torch.sum(seq * sim, 1)
+    def forward(self, seq, query=None):
+        if self.mode == 'weighted_sum':
+            w = F.softmax(torch.matmul(seq, query.transpose(1, 2)), dim=1)
+            return (seq * w.expand(-1, -1, seq.shape[2])).sum(1)
+        red = {'avg': torch.mean, 'max': torch.amax, 'min': torch.amin}[self.mode]
+        return red(seq, 1)
 
 
 class Discriminator(nn.Module):
-    """Constructed (never called) by Model so that checkpoints and RNG order line up (model.py:76-105,131)."""
+    """Only the constructor matters: Model creates it so that ``disc.f_k.{weight,bias}`` exist in the state_dict and
+    the seeded initialisation order matches (model.py:76-90,131).  The reference never calls it on the GGAD path."""
 
     def __init__(self, n_h, negsamp_round):
         super(Discriminator, self).__init__()
         self.f_k = nn.Bilinear(n_h, n_h, 1)
-        for m in self.modules():
-            if isinstance(m, nn.Bilinear):
-                torch.nn.init.xavier_uniform_(m.weight.data)
-                if m.bias is not None:
-                    m.bias.data.fill_(0.0)
+        torch.nn.init.xavier_uniform_(self.f_k.weight.data)
+        if self.f_k.bias is not None:
+            self.f_k.bias.data.fill_(0.0)
         self.negsamp_round = negsamp_round
-
-    def forward(self, c, h_pl):
-        scs = [self.f_k(h_pl, c)]
-        c_mi = c
-        for _ in range(self.negsamp_round):
-            c_mi = torch.cat((c_mi[-2:-1, :], c_mi[:-1, :]), 0)
-            scs.append(self.f_k(h_pl, c_mi))
-        return torch.cat(tuple(scs))
 
 
 class Model(nn.Module):
@@ -156,14 +145,8 @@ class Model(nn.Module):
         self.fc6 = nn.Linear(n_h, n_h, bias=False)
         self.fc5 = nn.Linear(n_h, n_in, bias=False)
         self.act = nn.ReLU()
-        if readout == 'max':
-            self.read = MaxReadout()
-        elif readout == 'min':
-            self.read = MinReadout()
-        elif readout == 'avg':
-            self.read = AvgReadout()
-        elif readout == 'weighted_sum':
-            self.read = WSReadout()
+        if readout in ('max', 'min', 'avg', 'weighted_sum'):
+            self.read = _Readout(readout)
         self.disc = Discriminator(n_h, negsamp_round)
 
     def _mlp(self, t):

@@ -36,7 +36,8 @@ def gather_reduce(g: CSRGraph, x: torch.Tensor, *, xmap: Optional[torch.Tensor] 
                   dot_mat: Optional[torch.Tensor] = None, dot_rows: Optional[torch.Tensor] = None,
                   dot_scale: Optional[torch.Tensor] = None, use_graph_scales: bool = True,
                   y_out: Optional[torch.Tensor] = None, y_peers=None, y_multicast: Optional[int] = None,
-                  peer_need: Optional[torch.Tensor] = None):
+                  peer_need: Optional[torch.Tensor] = None, chase: bool = False, chase_ctas: int = 0,
+                  mc_min_peers: int = 0):
     """Raw (non-autograd) call of ggad_gather_reduce.  ``x`` is [n_x_rows, d] fp32 CUDA with d % 4 == 0.
     Returns dict(y=, z=, sumsq=, dot=) with the requested outputs."""
     _lib.require_cuda(x, "x")
@@ -50,6 +51,17 @@ def gather_reduce(g: CSRGraph, x: torch.Tensor, *, xmap: Optional[torch.Tensor] 
     if use_graph_scales:
         row_scale = g.row_scale if row_scale is None else row_scale
         col_scale = g.col_scale if col_scale is None else col_scale
+    # shape contract (the device code trusts it: a short operand would be a silent out-of-bounds gather where the
+    # reference's bmm / spmm raises a shape error)
+    if xmap is not None:
+        if xmap.numel() < g.n_cols or xmap.dtype != torch.int32 or not xmap.is_cuda:
+            raise RuntimeError(f"ggad_b200: xmap must be an int32 CUDA vector with >= n_cols={g.n_cols} entries")
+    elif x.shape[0] < g.n_cols:
+        raise RuntimeError(f"ggad_b200: operand has {x.shape[0]} rows but the graph has {g.n_cols} columns")
+    for nm, t, need in (("row_scale", row_scale, n), ("col_scale", col_scale, g.n_cols), ("dot_rows", dot_rows, n),
+                        ("dot_scale", dot_scale, n), ("bias", bias, d)):
+        if t is not None and (t.numel() < need or not t.is_cuda):
+            raise RuntimeError(f"ggad_b200: {nm} needs >= {need} CUDA elements, got {t.numel()} on {t.device}")
     if y_out is not None:
         assert y_out.shape == (n, d) and y_out.dtype == torch.float32 and y_out.stride(0) == d and y_out.is_cuda
     y = (y_out if y_out is not None else torch.empty(n, d, dtype=torch.float32, device=dev)) if want_y else None
@@ -77,15 +89,53 @@ def gather_reduce(g: CSRGraph, x: torch.Tensor, *, xmap: Optional[torch.Tensor] 
         if peer_need is not None:     # halo exchange: int32 bit mask per row, bit p = y_peers[p] gathers the row
             assert peer_need.dtype == torch.int32 and peer_need.numel() == n and peer_need.is_cuda
             desc.peer_need = ptr(peer_need)
-    if y_multicast:
+    if y_multicast and not chase:
         desc.y_multicast = int(y_multicast)
     plan = g.plan
     if plan is not None:
         ws = g.workspace(d)
         desc.tile_row, desc.tile_edge, desc.n_tiles, desc.ws = ptr(plan[0]), ptr(plan[1]), plan[2], ptr(ws)
+    if not (chase and y_peers):
+        with torch.cuda.device(dev):
+            check(lib().ggad_gather_reduce(desc, stream_ptr(dev)))
+        return dict(y=y, z=z, sumsq=ss, dot=dot)
+    # ---- chase mode: the gather only flags finished tiles; the exchange runs beside it as ggad_halo_chase on a
+    # second, higher-priority stream (enqueued AFTER the gather, so a serialising launch order is still correct)
+    if plan is None or y is None:
+        raise RuntimeError("ggad_b200: chase exchange needs the merge-path plan and the local y")
+    done, epoch = g.chase_flags()
+    desc.tile_done, desc.tile_epoch = ptr(done), epoch
+    cd = _lib.ChaseDesc()
+    cd.y, cd.ldy, cd.d, cd.n_peer = ptr(y), d, d, len(y_peers)
+    cd.rowptr, cd.n_rows = ptr(g.rowptr), g.n_rows
+    cd.tile_row, cd.tile_edge, cd.n_tiles = ptr(plan[0]), ptr(plan[1]), plan[2]
+    cd.tile_done, cd.tile_epoch, cd.n_ctas = ptr(done), epoch, int(chase_ctas)
+    cd.peer_need = ptr(peer_need)
+    for i, pp in enumerate(y_peers):
+        cd.y_peer[i] = int(pp)
+    if y_multicast and mc_min_peers > 0:
+        cd.y_multicast, cd.mc_min_peers = int(y_multicast), int(mc_min_peers)
+    cur = torch.cuda.current_stream(dev)
+    side = _chase_stream(dev)
     with torch.cuda.device(dev):
-        check(lib().ggad_gather_reduce(desc, stream_ptr(dev)))
+        side.wait_stream(cur)                       # everything the gather waits for, the chase waits for too
+        check(lib().ggad_gather_reduce(desc, cur.cuda_stream))
+        check(lib().ggad_halo_chase(cd, side.cuda_stream))
+        y.record_stream(side)
+        cur.wait_stream(side)
     return dict(y=y, z=z, sumsq=ss, dot=dot)
+
+
+_chase_streams = {}
+
+
+def _chase_stream(dev) -> torch.cuda.Stream:
+    key = torch.device(dev).index
+    s = _chase_streams.get(key)
+    if s is None:
+        s = torch.cuda.Stream(device=dev, priority=-1)   # high priority: its few CTAs take the next free SM slots
+        _chase_streams[key] = s
+    return s
 
 
 def halo_push(y: torch.Tensor, y_peers, peer_need: Optional[torch.Tensor] = None) -> None:
@@ -151,7 +201,7 @@ class _GcnAggregate(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         z, slope = ctx.saved_tensors
-        neg = z < 0
+        neg = ~(z > 0)                      # torch's PReLU backward: x > 0 ? g : w * g  (so z == 0 takes the slope)
         dz = torch.where(neg, dy * slope, dy)
         dslope = (dy * z * neg).sum().reshape(slope.shape) if ctx.needs_input_grad[3] else None
         dbias = dz.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None

@@ -124,12 +124,17 @@ typedef struct ggad_gather_desc {
    * (barrier) before anyone reads the replicated matrix. */
   float* y_peer[7];
   int32_t n_peer;
-  int32_t reserved;
+  int32_t tile_epoch; /* chase mode (tile_done below): value published per finished tile, != the buffer's old contents */
   float* y_multicast; /* NULL or multicast address covering all ranks (used instead of y_peer) */
   /* halo exchange: NULL (every row goes to every peer) or [n_rows] bit masks -- bit p set means y_peer[p]
    * gathers row r in its next pass (the row is a column of that peer's CSR shard), so only those rows
    * cross NVLink.  Rows a peer does not need are left untouched in its replica. */
   const uint32_t* peer_need;
+  /* chase mode: NULL, or [n_tiles] flags (needs the plan and y_peer/peer_need as above).  The tiled kernel then
+   * does NOT push its rows itself; every CTA publishes tile_done[k] = tile_epoch (release, GPU scope) once the rows
+   * its tile finished are in y, and a concurrently running ggad_halo_chase moves them over NVLink from a few SMs
+   * of its own.  Rows cut by tile boundaries are still pushed by the fix-up kernel of this launch. */
+  int32_t* tile_done;
 } ggad_gather_desc_t;
 
 GGAD_API int ggad_gather_reduce(const ggad_gather_desc_t* desc, ggad_stream_t stream);
@@ -142,6 +147,36 @@ GGAD_API int ggad_gather_reduce(const ggad_gather_desc_t* desc, ggad_stream_t st
  * step of the destination-range sharded layer pass. */
 GGAD_API int ggad_halo_push(const float* y, int64_t ldy, int64_t n_rows, int32_t d, const uint32_t* peer_need,
                             float* const* y_peer_host, int32_t n_peer, ggad_stream_t stream);
+
+/* Exchange half of the chase mode: a persistent kernel (n_ctas CTAs, 0 = default) to be enqueued on a SECOND,
+ * higher-priority stream right AFTER the ggad_gather_reduce launch that carries the same tile_done / tile_epoch.
+ * Warp w waits (acquire, bounded spin) for tile_done[k] == tile_epoch of tiles k = w, w + W, ... and copies the
+ * rows that tile finished -- [tile_row[k] (+1 if that row began in an earlier tile), tile_row[k+1]) -- from y
+ * into the peers selected by peer_need, exactly as the in-kernel push does.  A row whose mask has at least
+ * mc_min_peers bits set is instead stored ONCE through the NVSwitch multicast address y_multicast (if non-NULL;
+ * multimem.st lands in every rank's replica, which is harmless for ranks that do not gather the row).
+ * Deadlock-free in every launch order: enqueued after the gather it can at worst run after it (no overlap).
+ * The reference has no multi-GPU path. */
+typedef struct ggad_chase_desc {
+  const float* y; /* this rank's rows of the replicated matrix (same pointer as the gather's y) */
+  int64_t ldy;
+  int32_t d;
+  int32_t n_peer;
+  const int64_t* rowptr; /* CSR of the gather launch (to tell whether a tile's first row began earlier) */
+  int64_t n_rows;
+  const int32_t* tile_row;
+  const int64_t* tile_edge;
+  int64_t n_tiles;
+  const int32_t* tile_done;
+  int32_t tile_epoch;
+  int32_t n_ctas;
+  const uint32_t* peer_need; /* NULL = every row to every peer */
+  float* y_peer[7];
+  float* y_multicast;
+  int32_t mc_min_peers; /* <= 0: never multicast */
+  int32_t reserved;
+} ggad_chase_desc_t;
+GGAD_API int ggad_halo_chase(const ggad_chase_desc_t* desc, ggad_stream_t stream);
 
 /* Merge-path plan for a CSR: n_tiles = ceil((n_rows + nnz) / GGAD_TILE_ITEMS). */
 GGAD_API int64_t ggad_plan_num_tiles(int64_t n_rows, int64_t nnz);

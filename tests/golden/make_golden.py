@@ -59,7 +59,11 @@ def _ref_normalize_adj(adj):
 
 # ----------------------------------------------------------------------------
 def make_graph(kind, n, rng):
-    if kind == "sym_binary":
+    if kind == "sym_binary_big":       # large enough that every operator of the case runs the merge-path tiled kernel
+        m = sp.random(n, n, density=20.0 / n, random_state=rng, data_rvs=lambda k: np.ones(k))
+        a = ((m + m.T) > 0).astype(np.float64)
+        a.setdiag(0)
+    elif kind == "sym_binary":
         m = sp.random(n, n, density=6.0 / n, random_state=rng, data_rvs=lambda k: np.ones(k))
         a = ((m + m.T) > 0).astype(np.float64)
         a.setdiag(0)
@@ -194,11 +198,11 @@ def make_adj_lists(n, avg_deg, rng, hub=None, isolated=()):
     return adj
 
 
-def minibatch_case(ref_sage, name, n, d, h, bsz, n_ab, seed, hub=None, dup=False):
+def minibatch_case(ref_sage, name, n, d, h, bsz, n_ab, seed, hub=None, dup=False, avg_deg=5.0):
     rng = np.random.default_rng(seed)
     torch.manual_seed(seed)
     random.seed(seed)
-    adj = make_adj_lists(n, 5.0, rng, hub=hub)
+    adj = make_adj_lists(n, avg_deg, rng, hub=hub)
     x = rng.random((n, d)).astype(np.float32)
     feats = nn.Embedding(n, d)
     feats.weight = nn.Parameter(torch.FloatTensor(x), requires_grad=False)   # model_handler.py:263-264
@@ -291,6 +295,10 @@ def main():
     minibatch_case(ref_sage, "mb_basic", 300, 17, 64, 40, 10, 72)
     minibatch_case(ref_sage, "mb_hub", 240, 10, 16, 32, 8, 0, hub=11)
     minibatch_case(ref_sage, "mb_dup", 200, 25, 32, 24, 6, 72, dup=True)
+    # cases whose operators cross ggad_b200.graph.PLAN_MIN_ITEMS (rows + edges >= 16 384), so the reference-derived
+    # goldens reach gather_tiled_kernel and not only the row-per-group kernel
+    full_batch_case(ref_model, "fb_big", "sym_binary_big", 3000, 24, 32, 0, 0.02, 0.01)
+    minibatch_case(ref_sage, "mb_big", 6000, 17, 64, 600, 150, 72, avg_deg=10.0)
     sage_case(ref_sage, "sage_concat", 150, 17, 32, 20, 0, gcn=False)
     sage_case(ref_sage, "sage_gcn", 150, 10, 16, 20, 72, gcn=True)
 

@@ -103,11 +103,15 @@ def test_gather_reduce_epilogues(use_plan, weighted):
 
 @pytest.mark.parametrize("d", [12, 64, 300])
 @pytest.mark.parametrize("epilogue", [False, True])
-def test_fused_exchange_push_single_gpu(d, epilogue):
-    """The fused exchange on ONE GPU: the "peers" are three local matrices, so the end-of-tile push phase
-    (and the fix-up kernel's peer stores for rows cut by tile boundaries) is checked bit-exactly without
-    NVLink: rows whose need bit is set equal y, all other rows stay untouched; no mask = every row."""
+@pytest.mark.parametrize("mode", ["tile", "chase"])
+def test_fused_exchange_push_single_gpu(d, epilogue, mode):
+    """The fused exchange on ONE GPU: the "peers" are three local matrices, so the exchange -- the end-of-tile push
+    phase (mode tile) or the concurrently running ggad_halo_chase kernel fed by tile-done flags (mode chase), plus
+    the fix-up kernel's peer stores for rows cut by tile boundaries -- is checked without NVLink: the local result
+    and every needed peer row equal the ORACLE's SpMM (rtol 1e-4), peers equal the local y bit for bit, all other
+    rows stay untouched; no mask = every row."""
     _, _, graph, ops, _ = _mods()
+    chase = dict(chase=True) if mode == "chase" else {}
     n_rows, n_cols = 6000, 5000
     rowptr, col, val = make_csr(n_rows, n_cols, 11.0, seed=d, hub=7000, weighted=epilogue)
     g = graph.CSRGraph.from_arrays(rowptr, col, val, n_rows, n_cols, use_plan=True)
@@ -117,14 +121,21 @@ def test_fused_exchange_push_single_gpu(d, epilogue):
     kw = dict(bias=torch.randn(d).cuda(), relu=True, want_sumsq=True) if epilogue else {}
     y_ref = ops.gather_reduce(g, x, **kw)["y"]
     peers = [torch.full((n_rows, d), float("nan"), device="cuda") for _ in range(3)]
-    y = ops.gather_reduce(g, x, y_peers=[p.data_ptr() for p in peers], peer_need=need, **kw)["y"]
+    y = ops.gather_reduce(g, x, y_peers=[p.data_ptr() for p in peers], peer_need=need, **chase, **kw)["y"]
+    torch.cuda.synchronize()
     assert torch.equal(y, y_ref)
+    o = oracle.spmm_csr(rowptr, col, val, x.cpu())
+    if epilogue:
+        o = torch.relu(o + kw["bias"].cpu())
+    assert_close(y, o, rtol=RTOL, atol=3e-4, what=f"PEER variant vs oracle ({mode})")
     for s_, p in enumerate(peers):
         sel = ((need >> s_) & 1).bool()
         assert torch.equal(p[sel], y_ref[sel]), f"peer {s_}: needed rows differ"
         assert bool(torch.isnan(p[~sel]).all()), f"peer {s_}: rows nobody asked for were written"
     full = [torch.full((n_rows, d), float("nan"), device="cuda") for _ in range(2)]
-    ops.gather_reduce(g, x, y_peers=[p.data_ptr() for p in full], **kw)
+    for _ in range(3):                          # repeated launches: the chase epochs advance, flags are never reset
+        ops.gather_reduce(g, x, y_peers=[p.data_ptr() for p in full], **chase, **kw)
+    torch.cuda.synchronize()
     assert all(torch.equal(p, y_ref) for p in full)
 
 
@@ -436,3 +447,81 @@ def test_errors_are_loud():
     desc.n_rows, desc.d = 5, 8                                               # null pointers
     assert _lib.lib().ggad_gather_reduce(C.byref(desc), None) == -1          # GGAD_ERR_INVALID, no crash
     assert b"required" in _lib.lib().ggad_last_error()
+
+
+# ------------------------------------------------------------------------------------------
+# the merge-path tiled kernel at the BASELINE.json shapes (plan ON), against scipy's CSR matmul in fp64
+# ------------------------------------------------------------------------------------------
+def _sym_graph(n, nnz_target, seed):
+    """Symmetric binary adjacency with ~nnz_target stored entries and a power-law degree profile (host)."""
+    rng = np.random.default_rng(seed)
+    m = nnz_target // 2
+    w = (1.0 - rng.random(n)) ** (-1.0 / 1.5)
+    src = rng.choice(n, m, p=w / w.sum())
+    dst = rng.integers(0, n, m)
+    keep = src != dst
+    a = sp.coo_matrix((np.ones(keep.sum()), (src[keep], dst[keep])), shape=(n, n)).tocsr()
+    return ((a + a.T) > 0).astype(np.float64).tocsr()
+
+
+def _bound_check(got, ref64, mag64, what):
+    """|got - ref| <= 1e-4 |ref| + 1e-5 sum|terms| elementwise (fp32 rounding of a long sum scales with its terms)."""
+    err = np.abs(got.double().cpu().numpy() - ref64)
+    bound = 1e-4 * np.abs(ref64) + 1e-5 * mag64 + 1e-30
+    worst = float((err / bound).max())
+    assert worst <= 1.0, f"{what}: max err/bound {worst:.3f}"
+
+
+@pytest.mark.parametrize("name,n,nnz,d", [("C2-L1", 11944, 4_398_392, 28), ("C2-L2", 11944, 4_398_392, 300),
+                                          ("C3-L1", 39357, 21_222_543, 12)])
+def test_tiled_kernel_at_full_batch_config_shapes(name, n, nnz, d):
+    """C2 (Amazon-shaped) and C3 (T-Finance-shaped): A_hat built exactly as run.py:96-109 (graph.full_batch_graphs,
+    weighted -> MODE 1), forward and the autograd backward (transposed CSR) of ops.spmm against scipy in fp64."""
+    _, _, graph, ops, _ = _mods()
+    a = _sym_graph(n, nnz, seed=len(name))
+    g_hat, g_r = graph.full_batch_graphs(a)
+    assert g_hat.plan is not None and g_hat.nnz + n >= graph.PLAN_MIN_ITEMS
+    a_hat = (oracle.normalize_adj(a) + sp.eye(n)).tocsr().astype(np.float32).astype(np.float64)
+    x = torch.randn(n, d)
+    xd = x.cuda().requires_grad_(True)
+    y = ops.spmm(g_hat, xd)
+    _bound_check(y.detach(), a_hat @ x.double().numpy(), abs(a_hat) @ x.double().abs().numpy(), name + " forward")
+    dy = torch.randn(n, d)
+    y.backward(dy.cuda())
+    _bound_check(xd.grad, a_hat.T @ dy.double().numpy(), abs(a_hat.T) @ dy.double().abs().numpy(), name + " backward")
+    # the GCN-layer launch (bias + PReLU + pre-activation in the epilogue) on the same operator
+    bias, slope = torch.randn(d), torch.tensor([0.25])
+    r = ops.gather_reduce(g_hat, ops.pad_cols(x.cuda()), bias=ops.pad_cols(bias.cuda().reshape(1, -1)).reshape(-1),
+                          prelu_slope=slope.cuda(), want_z=True)
+    z64 = a_hat @ x.double().numpy() + bias.double().numpy()
+    _bound_check(r["z"][:, :d], z64, abs(a_hat) @ x.double().abs().numpy() + 1.0, name + " z")
+    _bound_check(r["y"][:, :d], np.where(z64 > 0, z64, 0.25 * z64), abs(a_hat) @ x.double().abs().numpy() + 1.0, name + " y")
+
+
+def test_tiled_kernel_at_c4_slice():
+    """C4 (DGraph-shaped, d = 17 padded to 20): a 400 k-row destination slice over the full 3.7 M-row feature table
+    (296 MB, far beyond L2), mean aggregation (MODE 0 + row_scale) and the xmap path the mini-batch blocks use."""
+    _, _, graph, ops, _ = _mods()
+    n_cols, n_rows, nnz, d = 3_700_550, 400_000, 8_000_000, 20
+    rng = np.random.default_rng(4)
+    w = (1.0 - rng.random(n_rows)) ** (-1.0 / 1.1)
+    deg = np.minimum(rng.multinomial(nnz, w / w.sum()), 100_000)
+    rowptr = np.zeros(n_rows + 1, np.int64)
+    np.cumsum(deg, out=rowptr[1:])
+    col = rng.integers(0, n_cols, rowptr[-1]).astype(np.int32)
+    inv = np.where(deg > 0, 1.0 / np.maximum(deg, 1), 0).astype(np.float32)
+    g = graph.CSRGraph.from_arrays(rowptr, col, None, n_rows, n_cols, use_plan=True)
+    g.row_scale = torch.from_numpy(inv).cuda()
+    x = torch.rand(n_cols, 17)
+    xp = ops.pad_cols(x.cuda())
+    assert xp.shape[1] == d
+    a = sp.csr_matrix((np.ones(len(col)), col, rowptr), shape=(n_rows, n_cols))
+    ref = sp.diags(inv.astype(np.float64)) @ (a @ x.double().numpy())
+    y = ops.gather_reduce(g, xp)["y"]
+    _bound_check(y[:, :17], ref, np.abs(ref), "C4 slice mean aggregation")       # all terms >= 0: sum|terms| = ref
+    assert bool((y[:, 17:] == 0).all())
+    perm = torch.randperm(n_cols)
+    table = torch.empty_like(xp)
+    table[perm.cuda()] = xp                                                        # row c of x lives at table[perm[c]]
+    y2 = ops.gather_reduce(g, table, xmap=perm.to(torch.int32).cuda())["y"]
+    assert torch.equal(y2, y)                                                      # same order of summation: bit-exact
