@@ -19,6 +19,8 @@
 // Roofline: HBM-bound (<= 0.5 flop/B).  Algorithmic bytes per launch
 //   nnz*(4 + 4*[val]) + (n_rows+1)*8 + n_x_rows*d*4 + n_rows*d*4      
 #pragma once
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ggad {
@@ -93,10 +95,10 @@ __device__ __forceinline__ void store_y(const GatherArgs& a, int64_t r, int ch, 
 // Full per-row epilogue (bias / activation / z / sumsq / dot).  It is large, so kernels that use it keep the
 // number of inlined copies at two (rolled boundary path below); a non-inlined call was measured slower
 // (register spills around the call sites), 17 inlined copies 2x slower (instruction cache).
-template <int G, int CH, bool PEER>
+template <int G, int CH, bool PEER, bool PRESCALED = false>
 __device__ __forceinline__ void finish_row_full(const GatherArgs& a, int64_t r, const float4* acc, int gl, unsigned gmask) {
   const int V = a.d >> 2;
-  const float rs = a.row_scale ? __ldg(a.row_scale + r) : 1.f;
+  const float rs = (!PRESCALED && a.row_scale) ? __ldg(a.row_scale + r) : 1.f;
   const bool want_dot = a.dot_out != nullptr;
   const bool want_ss = a.sumsq != nullptr;
   const float4* dm = nullptr;
@@ -148,12 +150,60 @@ __device__ __forceinline__ void finish_row_full(const GatherArgs& a, int64_t r, 
 }
 
 
-template <int G, int CH, bool FULL = true, bool PEER = false>
-__device__ __forceinline__ void finish_row(const GatherArgs& a, int64_t r, const float4 (&acc)[CH], int gl,
-                                           unsigned gmask) {
+// Epilogue kinds (template parameter EPI of the tiled kernel):
+//   0 plain   y = row_scale * acc
+//   1 light   elementwise only: + bias, optional pre-activation store z, PReLU / ReLU -- the GCN-layer launch of
+//             model.py:29-35.  Small enough to be inlined at every row end like the plain one (bias comes from shared
+//             memory, the slope from a register), so the launch keeps the unrolled gather loop.
+//   2 full    additionally |y|^2 and the dot epilogue (group shuffles); rolled boundary walk, three inlined copies.
+//   3 deferred  the gather loop is the plain one (y = row_scale * acc at every row end); after its loop every lane
+//             group re-reads the rows it finished (its own stores: same thread, same address; L2 hits, two rows in
+//             flight) and applies the full epilogue in ONE rolled loop.  Costs one extra L2 read of y but keeps the
+//             hot loop identical to the plain kernel whatever the epilogue asks for.  Needs the y output.
+struct EpiRegs {
+  const float* s_bias;  // shared memory, d floats (zeros when there is no bias)
+  float slope;
+  int act;              // 0 none, 1 ReLU, 2 PReLU
+};
+
+template <int G, int CH, bool PEER>
+__device__ __forceinline__ void finish_row_light(const GatherArgs& a, int64_t r, const float4 (&acc)[CH], int gl,
+                                                 const EpiRegs& ep) {
   const int V = a.d >> 2;
   const float rs = a.row_scale ? __ldg(a.row_scale + r) : 1.f;
-  if (!FULL) {  // plain SpMM: y = row_scale * acc, nothing else requested
+#pragma unroll
+  for (int j = 0; j < CH; ++j) {
+    const int ch = gl + G * j;
+    if (ch < V) {
+      float4 v = acc[j];
+      const float4 b = reinterpret_cast<const float4*>(ep.s_bias)[ch];
+      // multiply, round, add: the same two roundings as the full epilogue and the reference (A x rounded, + bias)
+      v.x = __fadd_rn(__fmul_rn(v.x, rs), b.x); v.y = __fadd_rn(__fmul_rn(v.y, rs), b.y);
+      v.z = __fadd_rn(__fmul_rn(v.z, rs), b.z); v.w = __fadd_rn(__fmul_rn(v.w, rs), b.w);
+      if (a.z) stg_cs_f4(reinterpret_cast<float4*>(a.z + r * a.ldy) + ch, v);
+      if (ep.act == 2) {
+        v.x = v.x >= 0.f ? v.x : ep.slope * v.x;
+        v.y = v.y >= 0.f ? v.y : ep.slope * v.y;
+        v.z = v.z >= 0.f ? v.z : ep.slope * v.z;
+        v.w = v.w >= 0.f ? v.w : ep.slope * v.w;
+      } else if (ep.act == 1) {
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+      }
+      store_y<PEER>(a, r, ch, v);
+    }
+  }
+}
+
+template <int G, int CH, int EPI = 2, bool PEER = false>
+__device__ __forceinline__ void finish_row(const GatherArgs& a, int64_t r, const float4 (&acc)[CH], int gl,
+                                           unsigned gmask, const EpiRegs& ep = EpiRegs{nullptr, 0.f, 0}) {
+  const int V = a.d >> 2;
+  if (EPI == 1) {
+    finish_row_light<G, CH, PEER>(a, r, acc, gl, ep);
+    return;
+  }
+  const float rs = a.row_scale ? __ldg(a.row_scale + r) : 1.f;
+  if (EPI == 0 || EPI == 3) {  // plain SpMM: y = row_scale * acc (EPI 3: the epilogue follows in post_rows)
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       const int ch = gl + G * j;
@@ -273,6 +323,11 @@ __device__ __forceinline__ void push_rows(const GatherArgs& a, int64_t ra, int64
 #ifndef GGAD_PUSH_PER_GROUP
 #define GGAD_PUSH_PER_GROUP 0
 #endif
+// A/B knob: 1 = the light epilogue (EPI 1) also uses the rolled boundary walk of the full one (3 inlined copies,
+// ~30 KB of code) instead of the plain kernel's unrolled walk (17 copies, ~49 KB)
+#ifndef GGAD_LIGHT_ROLLED
+#define GGAD_LIGHT_ROLLED 0
+#endif
 template <int G, int CH>
 __device__ __forceinline__ void push_group_rows(const GatherArgs& a, int64_t ra, int64_t rb, int gl) {
   if (a.y == nullptr) return;
@@ -311,10 +366,33 @@ __device__ __forceinline__ void push_group_rows(const GatherArgs& a, int64_t ra,
   }
 }
 
+// Deferred epilogue (EPI 3): rows [ra, rb) were finished by THIS lane group as y = row_scale * acc; every lane
+// re-reads exactly the chunks it stored itself, two rows in flight, and runs the full epilogue on them.
+template <int G, int CH, bool PEER>
+__device__ __forceinline__ void post_rows(const GatherArgs& a, int64_t ra, int64_t rb, int gl, unsigned gmask) {
+  if (ra >= rb) return;
+  const int V = a.d >> 2;
+  auto load_row = [&](int64_t r, float4 (&v)[CH]) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const int ch = gl + G * j;
+      v[j] = (ch < V) ? __ldcg(reinterpret_cast<const float4*>(a.y + r * a.ldy) + ch) : f4_zero();
+    }
+  };
+  float4 cur[CH], nxt[CH];
+  load_row(ra, cur);
+  for (int64_t r = ra; r < rb; ++r) {   // one epilogue copy; the next row's load is in flight while this one finishes
+    if (r + 1 < rb) load_row(r + 1, nxt);
+    finish_row_full<G, CH, PEER, true>(a, r, cur, gl, gmask);
+#pragma unroll
+    for (int j = 0; j < CH; ++j) cur[j] = nxt[j];
+  }
+}
+
 // ---------------------------------------------------------------------------
 // merge-path tiled kernel
 // ---------------------------------------------------------------------------
-template <int G, int CH, bool HASVAL = true>
+template <int G, int CH, bool HASVAL = true, bool BIAS = false>
 struct TileSmem {
   static constexpr int NGRP = kThreads / G;
   static constexpr int kBar = 0;                                   // uint64 mbarrier (+pad)
@@ -325,15 +403,16 @@ struct TileSmem {
   static constexpr int kCj = kCi + ((NGRP + 1 + 3) / 4) * 16;      // int32[NGRP + 1] (+pad)
   static constexpr int kFlag = kCj + ((NGRP + 1 + 3) / 4) * 16;    // int32[NGRP] (+pad)
   static constexpr int kPart = kFlag + ((NGRP + 3) / 4) * 16;      // float4[NGRP][2][G*CH]
-  static constexpr int kBytes = kPart + NGRP * 2 * G * CH * 16;
+  static constexpr int kBias = kPart + NGRP * 2 * G * CH * 16;     // float4[G*CH] bias row (light epilogue only)
+  static constexpr int kBytes = kBias + (BIAS ? G * CH * 16 : 0);
 };
 
 // MODE 0: unweighted (val == NULL), 1: per-edge val, 2: general (col_scale / xmap, optional val).
 // EPI false: plain y = row_scale * acc; true: bias / activation / z / sumsq / dot epilogue.
 // PEER: the epilogue also stores every finished row to the peers' replicas / the multicast address.
-template <int G, int CH, int MODE, bool EPI, bool PEER>
+template <int G, int CH, int MODE, int EPI, bool PEER>
 __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2)) gather_tiled_kernel(const __grid_constant__ GatherArgs a) {
-  using L = TileSmem<G, CH, MODE != 0>;
+  using L = TileSmem<G, CH, MODE != 0, EPI == 1>;
   constexpr int NGRP = L::NGRP;
   constexpr int U = (CH == 1) ? 8 : (CH == 2 ? 4 : 2);
   extern __shared__ __align__(16) unsigned char smem[];
@@ -381,6 +460,14 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
   }
   // start of row r0 relative to the tile (<= 0; < 0 means the row began in an earlier tile)
   const int rstart0 = (r0 < a.n_rows) ? int(__ldg(a.rowptr + r0) - e0) : 0;
+  EpiRegs ep{nullptr, 0.f, 0};
+  if constexpr (EPI == 1) {
+    float* s_bias = reinterpret_cast<float*>(smem + L::kBias);
+    for (int t = tid; t < G * CH * 4; t += kThreads) s_bias[t] = (a.bias && t < a.d) ? __ldg(a.bias + t) : 0.f;
+    ep.s_bias = s_bias;
+    ep.act = a.prelu_slope ? 2 : (a.relu ? 1 : 0);
+    ep.slope = a.prelu_slope ? __ldg(a.prelu_slope) : 0.f;
+  }
   __syncthreads();
 
   // ---- second-level merge path: split (nr + ne) items evenly over the NGRP groups ----
@@ -412,9 +499,8 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
     int row = i1;
     int cur_end = s_rend[row];
     bool head_pending = ((i1 == 0) ? rstart0 : s_rend[i1 - 1]) < j1;  // first row began before this group
-#if GGAD_PUSH_PER_GROUP
     const bool head0 = head_pending;
-#endif
+    (void)head0;
     int flag = 0;
     float4 acc[CH];
     // Byte offset of this lane's 16-byte chunk(s) inside a row.  Lanes beyond the row width (V not a
@@ -441,7 +527,7 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
         flag |= 1;
         head_pending = false;
       } else {
-        finish_row<G, CH, EPI, false>(a, r0 + row, acc, gl, gmask);
+        finish_row<G, CH, EPI, false>(a, r0 + row, acc, gl, gmask, ep);
       }
 #pragma unroll
       for (int j = 0; j < CH; ++j) acc[j] = f4_zero();
@@ -456,7 +542,7 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
       }
     };
 
-    if constexpr (EPI) {
+    if constexpr (EPI == 2 || (EPI == 1 && GGAD_LIGHT_ROLLED)) {
       // Large epilogue: a batch that crosses row ends (and the ragged last batch) walks its rows in a rolled
       // loop, so only three inlined copies of the epilogue exist in the kernel.
       auto walk_rows = [&](int e, int nb, const float (&w)[U], const float4 (&xv)[U][CH]) {
@@ -574,6 +660,7 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
       flag |= 2;
     }
     if (gl == 0) s_flag[g] = flag;
+    if constexpr (EPI == 3) post_rows<G, CH, false>(a, r0 + i1 + (head0 ? 1 : 0), r0 + i2, gl, gmask);
 #if GGAD_PUSH_PER_GROUP
     if constexpr (PEER) push_group_rows<G, CH>(a, r0 + i1 + (head0 ? 1 : 0), r0 + i2, gl);
 #endif
@@ -599,7 +686,7 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
           for (int j = 0; j < CH; ++j)
             if (gl + G * j < V) reinterpret_cast<float4*>(ws_head)[gl + G * j] = chain[j];
         } else {
-          finish_row<G, CH, EPI, (GGAD_PUSH_PER_GROUP != 0) && PEER>(a, r0 + row, chain, gl, gmask);
+          finish_row<G, CH, (EPI == 3) ? 2 : EPI, (GGAD_PUSH_PER_GROUP != 0) && PEER>(a, r0 + row, chain, gl, gmask, ep);
         }
 #pragma unroll
         for (int j = 0; j < CH; ++j) chain[j] = f4_zero();
@@ -635,7 +722,7 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
 
 // Finish rows that were cut by tile boundaries: one lane group per tile whose first row began earlier.
 template <int G, int CH, bool EPI, bool PEER>
-__global__ void __launch_bounds__(kThreads) tile_fixup_kernel(const __grid_constant__ GatherArgs a) {
+__global__ void __launch_bounds__(kThreads) tile_fixup_kernel(const __grid_constant__ GatherArgs a) {  // EPI: any epilogue (full code)
   const int64_t k = (int64_t(blockIdx.x) * kThreads + threadIdx.x) / G;
   if (k >= a.n_tiles) return;
   const int gl = threadIdx.x % G;
@@ -659,15 +746,15 @@ __global__ void __launch_bounds__(kThreads) tile_fixup_kernel(const __grid_const
 #pragma unroll
   for (int j = 0; j < CH; ++j)
     if (gl + G * j < V) f4_add(acc[j], h[gl + G * j]);
-  finish_row<G, CH, EPI, PEER>(a, r0, acc, gl, gmask);
+  finish_row<G, CH, EPI ? 2 : 0, PEER>(a, r0, acc, gl, gmask);
 }
 
 // ---------------------------------------------------------------------------
 // host dispatch
 // ---------------------------------------------------------------------------
-template <int G, int CH, int MODE, bool EPI, bool PEER>
+template <int G, int CH, int MODE, int EPI, bool PEER>
 static int launch_tiled(const GatherArgs& a, cudaStream_t st) {
-  using L = TileSmem<G, CH, MODE != 0>;
+  using L = TileSmem<G, CH, MODE != 0, EPI == 1>;
   // the attribute is per device (context), so the "already set" flag is too -- per instantiation and device
   static bool attr_done[64] = {};
   int dev = 0;
@@ -680,13 +767,13 @@ static int launch_tiled(const GatherArgs& a, cudaStream_t st) {
   gather_tiled_kernel<G, CH, MODE, EPI, PEER><<<(unsigned)a.n_tiles, kThreads, L::kBytes, st>>>(a);
   GGAD_CUDA_OK(cudaGetLastError());
   const int64_t fix_blocks = (a.n_tiles * G + kThreads - 1) / kThreads;
-  tile_fixup_kernel<G, CH, EPI, PEER><<<(unsigned)fix_blocks, kThreads, 0, st>>>(a);
+  tile_fixup_kernel<G, CH, EPI != 0, PEER><<<(unsigned)fix_blocks, kThreads, 0, st>>>(a);
   GGAD_CUDA_OK(cudaGetLastError());
   count_launch(2);
   return GGAD_OK;
 }
 
-template <int G, int CH, bool EPI, bool PEER>
+template <int G, int CH, int EPI, bool PEER>
 static int launch_mode(const GatherArgs& a, cudaStream_t st) {
   if (a.xmap || a.col_scale) return launch_tiled<G, CH, 2, EPI, PEER>(a, st);
   if (a.val) return launch_tiled<G, CH, 1, EPI, PEER>(a, st);
@@ -699,9 +786,18 @@ int launch_variant(const GatherArgs& a, cudaStream_t st, int sm_count) {
   const bool gen = a.xmap || a.col_scale;
   const bool peer = a.n_peer > 0 || a.y_mc || a.tile_done;
   if (a.tile_row) {
-    const bool epi = a.bias || a.prelu_slope || a.relu || a.z || a.sumsq || a.dot_out || (!a.y && !a.y_mc);
-    if (peer) return epi ? launch_mode<G, CH, true, true>(a, st) : launch_mode<G, CH, false, true>(a, st);
-    return epi ? launch_mode<G, CH, true, false>(a, st) : launch_mode<G, CH, false, false>(a, st);
+    // epilogue kind: 2 = reductions (|y|^2, dot) or no y at all; 1 = elementwise only (bias / activation / z); 0 = plain
+    static const bool force_full = getenv("GGAD_FORCE_FULL_EPI") != nullptr;   // A/B knob (profiling only)
+    const int epi = (a.sumsq || a.dot_out || (!a.y && !a.y_mc) || (force_full && (a.bias || a.prelu_slope || a.relu || a.z)))
+                        ? 2 : ((a.bias || a.prelu_slope || a.relu || a.z) ? 1 : 0);
+    static const bool deferred = getenv("GGAD_EPI_DEFERRED") != nullptr;        // A/B knob: epilogue kind 3
+    if (deferred && epi != 0 && a.y) return peer ? launch_mode<G, CH, 3, true>(a, st) : launch_mode<G, CH, 3, false>(a, st);
+    if (peer) {
+      if (epi == 2) return launch_mode<G, CH, 2, true>(a, st);
+      return epi == 1 ? launch_mode<G, CH, 1, true>(a, st) : launch_mode<G, CH, 0, true>(a, st);
+    }
+    if (epi == 2) return launch_mode<G, CH, 2, false>(a, st);
+    return epi == 1 ? launch_mode<G, CH, 1, false>(a, st) : launch_mode<G, CH, 0, false>(a, st);
   }
   GGAD_REQUIRE(!peer, GGAD_ERR_UNSUPPORTED, "gather_reduce: peer / multicast stores need the merge-path plan");
   const int64_t gpb = kThreads / G;
