@@ -66,6 +66,7 @@ SIGNATURES = {
     "ggad_gather_reduce": (C.c_int, [C.POINTER(GatherDesc), _vp]),
     "ggad_halo_push": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp]),
     "ggad_halo_chase": (C.c_int, [C.POINTER(ChaseDesc), _vp]),
+    "ggad_dense_matmul": (C.c_int, [_i32, _i32, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _f, _f, _i32, _i32, _vp]),
     "ggad_plan_num_tiles": (_i64, [_i64, _i64]),
     "ggad_plan_build": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
     "ggad_normalize_backward": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _vp]),

@@ -21,6 +21,17 @@ NVCC_FLAGS = [
 ]
 
 
+def _cutlass_includes():
+    """Header-only CUTLASS / CuTe tree for the tcgen05 GEMM (dense_*.cu): vendored under site-packages in this image."""
+    import sysconfig
+    roots = [os.environ.get("CUTLASS_DIR")] + [os.path.join(sysconfig.get_paths()["purelib"], p)
+                                                for p in ("flashinfer/data/cutlass", "tilelang/3rdparty/cutlass")]
+    for r in roots:
+        if r and os.path.exists(os.path.join(r, "include", "cutlass", "gemm", "collective", "builders", "sm100_9xBF16_umma_builder.inl")):
+            return ["-I" + os.path.join(r, "include"), "-I" + os.path.join(r, "tools", "util", "include"), "-diag-suppress", "20012"]
+    raise RuntimeError("CUTLASS >= 4.x headers with the sm100 builders not found (set CUTLASS_DIR)")
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
         if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
@@ -47,9 +58,22 @@ def build_library(force: bool = False, verbose: bool = False, out: str = None, d
     objdir = os.path.join(HERE, "build" if not variant else "build_" + os.path.basename(out).replace(".so", ""))
     os.makedirs(objdir, exist_ok=True)
 
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + \
+              [os.path.join(HERE, "..", "include", "ggad_b200.h"), os.path.abspath(__file__)]
+    stamp = os.path.join(objdir, ".flags")
+    flags_now = " ".join(sorted(defines)) + "|" + " ".join(NVCC_FLAGS)
+    same_flags = os.path.exists(stamp) and open(stamp).read() == flags_now
+
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        # incremental: an object newer than its source and than the headers it can include is kept
+        deps = [os.path.join(CSRC, src)] + [h for h in headers
+                                            if src.startswith("dense") or not h.endswith("dense_cutlass.cuh")]
+        if same_flags and not force and os.path.exists(obj) and all(os.path.getmtime(obj) > os.path.getmtime(d) for d in deps):
+            return obj
         cmd = [nvcc, *NVCC_FLAGS, *["-D" + d for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
+        if src.startswith("dense_"):
+            cmd += _cutlass_includes()
         if verbose:
             cmd += ["-Xptxas", "-v"]
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -62,6 +86,8 @@ def build_library(force: bool = False, verbose: bool = False, out: str = None, d
 
     with ThreadPoolExecutor(min(len(SOURCES), os.cpu_count() or 4)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
+    with open(stamp, "w") as f:
+        f.write(flags_now)
     target = out if variant else LIB
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", target, *objs, "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -82,6 +82,8 @@ int rmat_keys_impl(uint64_t*, int64_t, int64_t, int32_t, int32_t, uint64_t, floa
 
 int halo_push_impl(const float*, int64_t, int64_t, int32_t, const uint32_t*, float* const*, int32_t, cudaStream_t);
 int halo_chase_impl(const ggad_chase_desc_t*, cudaStream_t);
+int dense_matmul_impl(int, int, int64_t, int64_t, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, float,
+                      float, int, int, cudaStream_t);
 
 int block_rowptr_impl(const int64_t*, const int32_t*, int64_t, const int32_t*, int64_t, int, int64_t*, int64_t*, cudaStream_t);
 int block_fill_impl(const int64_t*, const int32_t*, int64_t, const int32_t*, int64_t, int, const int64_t*, int32_t*,
@@ -210,6 +212,12 @@ GGAD_API int ggad_halo_push(const float* y, int64_t ldy, int64_t n_rows, int32_t
 
 GGAD_API int ggad_halo_chase(const ggad_chase_desc_t* desc, ggad_stream_t stream) {
   return halo_chase_impl(desc, (cudaStream_t)stream);
+}
+
+GGAD_API int ggad_dense_matmul(int32_t trans_a, int32_t trans_b, int64_t m, int64_t n, int64_t k, const float* a, int64_t lda,
+                               const float* b, int64_t ldb, float* c, int64_t ldc, float alpha, float beta, int32_t relu,
+                               int32_t path, ggad_stream_t stream) {
+  return dense_matmul_impl(trans_a, trans_b, m, n, k, a, lda, b, ldb, c, ldc, alpha, beta, relu, path, (cudaStream_t)stream);
 }
 
 GGAD_API int ggad_normalize_backward(const float* e, int64_t lde, const float* inv_norm, float* g, int64_t ldg, int64_t n_rows,

@@ -87,56 +87,92 @@ struct ChaseArgs {
   float* y_mc;
 };
 
-// One warp per tile (tiles w, w + W, ...): lane 0 waits for the tile's flag, then the warp streams the tile's
-// finished rows L2 -> registers -> peers, U independent 16-byte chunks per lane in flight.  Bound: NVLink egress.
+// A CTA takes batches of kChaseTiles consecutive tiles (batch b, b + gridDim, ...): its first threads wait for the
+// batch's flags in parallel, the masks of the rows those tiles finished are staged in shared memory and the needed
+// rows compacted into a list (warp ballots), then the 256 threads stream the listed rows L2 -> registers -> peers,
+// kChaseU rows per lane group in flight.  Per batch: three dependent L2 round trips + the copy itself, so a few dozen
+// CTAs keep up with the gather kernel.  Bound: NVLink egress.
+constexpr int kChaseTiles = 8;
+constexpr int kChaseRows = 2048;  // rows staged per round (a batch with more row ends takes several rounds)
+constexpr int kChaseU = 4;
+
 __global__ void __launch_bounds__(256, 4) halo_chase_kernel(const __grid_constant__ ChaseArgs a) {
-  constexpr int U = 4;
-  const int lane = threadIdx.x & 31;
-  const int64_t W = int64_t(gridDim.x) * (blockDim.x >> 5);
+  __shared__ uint32_t s_need[kChaseRows];
+  __shared__ uint16_t s_list[kChaseRows];
+  __shared__ int s_cnt;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int V = a.d >> 2;
+  // lanes per row: the smallest power of two >= V (capped at 32; wider rows loop over their chunks)
+  int L = 1;
+  while (L < V && L < 32) L <<= 1;
+  const int rows_per_step = 256 / L;
+  const int sub = tid / L, sl = tid % L;
   const uint32_t all = (1u << a.n_peer) - 1u;
-  for (int64_t k = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); k < a.n_tiles; k += W) {
-    if (lane == 0) {
+  for (int64_t kb = int64_t(blockIdx.x) * kChaseTiles; kb < a.n_tiles; kb += int64_t(gridDim.x) * kChaseTiles) {
+    const int64_t ke = (kb + kChaseTiles < a.n_tiles) ? kb + kChaseTiles : a.n_tiles;
+    if (tid < int(ke - kb)) {
       uint32_t spins = 0;
-      while (ld_acquire_gpu(a.tile_done + k) != a.epoch) {
-        __nanosleep(200);
-        if (++spins > (1u << 23)) asm volatile("trap;");  // seconds: the producer launch is missing -- fail, don't hang
+      while (ld_acquire_gpu(a.tile_done + kb + tid) != a.epoch) {
+        __nanosleep(100);
+        if (++spins > (1u << 24)) asm volatile("trap;");  // seconds: the producer launch is missing -- fail, don't hang
       }
     }
-    __syncwarp();
-    const int64_t r0 = __ldg(a.tile_row + k), r1 = __ldg(a.tile_row + k + 1);
-    if (r1 <= r0) continue;
-    // a first row that began in an earlier tile is finished (and pushed) by the fix-up kernel
-    const int64_t ra = r0 + ((r0 < a.n_rows && __ldg(a.rowptr + r0) < __ldg(a.tile_edge + k)) ? 1 : 0);
-    const int total = int(r1 - ra) * V;
-    for (int i0 = lane; i0 < total; i0 += 32 * U) {
-      float4 v[U];
-      uint32_t nd[U];
-      int64_t off[U];
+    __syncthreads();
+    const int64_t rbase = __ldg(a.tile_row + kb), rend = __ldg(a.tile_row + ke);
+    for (int64_t rr = rbase; rr < rend; rr += kChaseRows) {
+      const int nrow = int((rend - rr < kChaseRows) ? rend - rr : kChaseRows);
+      if (tid == 0) s_cnt = 0;
+      for (int j = tid; j < nrow; j += 256) s_need[j] = (a.need ? __ldg(a.need + rr + j) : 0xffffffffu) & all;
+      __syncthreads();
+      // a tile's first row that began in an earlier tile is finished (and pushed) by the fix-up kernel, not here
+      if (tid < int(ke - kb)) {
+        const int64_t r = __ldg(a.tile_row + kb + tid);
+        if (r >= rr && r < rr + nrow && r < a.n_rows && __ldg(a.rowptr + r) < __ldg(a.tile_edge + kb + tid)) s_need[r - rr] = 0u;
+      }
+      __syncthreads();
+      for (int j0 = 0; j0 < nrow; j0 += 256) {   // compact the needed rows (order is irrelevant)
+        const int j = j0 + tid;
+        const bool f = j < nrow && s_need[j] != 0u;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&s_cnt, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (f) s_list[base + __popc(bal & ((1u << lane) - 1u))] = uint16_t(j);
+      }
+      __syncthreads();
+      const int cnt = s_cnt;
+      for (int t0 = sub; t0 < cnt; t0 += rows_per_step * kChaseU) {
+        for (int c0 = sl; c0 < V; c0 += L) {      // one trip unless the row is wider than 32 chunks
+          float4 v[kChaseU];
+          uint32_t nd[kChaseU];
+          int64_t off[kChaseU];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = i0 + 32 * u;
-        nd[u] = 0u;
-        if (i < total) {
-          const int j = i / V;
-          nd[u] = (a.need ? __ldg(a.need + ra + j) : 0xffffffffu) & all;
-          off[u] = (ra + j) * a.ldy + int64_t(i - j * V) * 4;
-          // L2-coherent load: written by another SM moments ago; made visible by the acquire above
-          if (nd[u]) v[u] = __ldcg(reinterpret_cast<const float4*>(a.y + off[u]));
+          for (int u = 0; u < kChaseU; ++u) {
+            const int t = t0 + u * rows_per_step;
+            nd[u] = 0u;
+            if (t < cnt) {
+              const int j = s_list[t];
+              nd[u] = s_need[j];
+              off[u] = (rr + j) * a.ldy + int64_t(c0) * 4;
+              // L2-coherent load: written by another SM moments ago, made visible by the acquire above
+              v[u] = __ldcg(reinterpret_cast<const float4*>(a.y + off[u]));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kChaseU; ++u) {
+            if (!nd[u]) continue;
+            if (a.y_mc && __popc(nd[u]) >= a.mc_min) {
+              asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.y_mc + off[u]), "f"(v[u].x),
+                           "f"(v[u].y), "f"(v[u].z), "f"(v[u].w)
+                           : "memory");
+            } else {
+              for (int p = 0; p < a.n_peer; ++p)
+                if ((nd[u] >> p) & 1u) stg_peer_f4(reinterpret_cast<float4*>(a.peer[p] + off[u]), v[u]);
+            }
+          }
         }
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (!nd[u]) continue;
-        if (a.y_mc && __popc(nd[u]) >= a.mc_min) {
-          asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.y_mc + off[u]), "f"(v[u].x),
-                       "f"(v[u].y), "f"(v[u].z), "f"(v[u].w)
-                       : "memory");
-        } else {
-          for (int p = 0; p < a.n_peer; ++p)
-            if ((nd[u] >> p) & 1u) stg_peer_f4(reinterpret_cast<float4*>(a.peer[p] + off[u]), v[u]);
-        }
-      }
+      __syncthreads();   // s_need / s_list are reused by the next round / batch
     }
   }
 }
@@ -159,7 +195,7 @@ int halo_chase_impl(const ggad_chase_desc_t* d, cudaStream_t st) {
     GGAD_REQUIRE(p >= d->n_peer || (a.peer[p] && aligned16(a.peer[p])), GGAD_ERR_ALIGN, "halo_chase: y_peer[%d] null or unaligned", p);
   }
   int ctas = d->n_ctas > 0 ? d->n_ctas : 48;
-  if (int64_t(ctas) * 8 > d->n_tiles) ctas = int((d->n_tiles + 7) / 8);
+  if (int64_t(ctas) * kChaseTiles > d->n_tiles) ctas = int((d->n_tiles + kChaseTiles - 1) / kChaseTiles);
   halo_chase_kernel<<<(unsigned)ctas, 256, 0, st>>>(a);
   GGAD_CUDA_OK(cudaGetLastError());
   count_launch(1);

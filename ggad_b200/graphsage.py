@@ -190,7 +190,7 @@ class GraphSage(nn.Module):
         init.xavier_uniform_(self.weight)
 
     def forward(self, nodes):
-        return self.weight.mm(self.enc(nodes)).t()
+        return ops.linear(self.enc(nodes).t(), self.weight)
 
     def to_prob(self, nodes):
         return torch.sigmoid(self.forward(nodes))
@@ -248,7 +248,7 @@ class Encoder(nn.Module):
             combined = torch.cat((self.features(index), neigh_feats), dim=1)
         else:
             combined = neigh_feats
-        return F.relu(self.weight.mm(combined.t()))
+        return ops.linear(combined, self.weight, relu=True).t()          # ReLU(W . combined^T)  (:153)
 
 
 # ------------------------------------------------------------------------------------------
@@ -301,18 +301,18 @@ class GCNEncoder(nn.Module):
     def forward(self, nodes, label, train_flag):
         neigh_feats, neigh_feats_expand, mask = self.aggregator.forward(nodes, _LazyNeighs(self.adj_lists, nodes),
                                                                         self.adj_lists, train_flag)
-        combined = F.relu(self.weight.mm(neigh_feats.t()))                       # aggregate, then project (:412)
+        combined = ops.linear(neigh_feats, self.weight, relu=True).t()           # aggregate, then project (:412)
         to_feats_neigh = None
         anomaly_feat = None
         anomaly_feat_new = None
         combined_all = combined
         if train_flag == True:
             label = label.to(combined.device)
-            combined_expand = F.relu(self.weight.mm(neigh_feats_expand.t()))     # hop-1 frontier embeddings (:419)
-            to_feats_neigh = mask.mm(combined_expand.t())                        # ego-neighbor mean (:421)
+            emb_u = ops.linear(neigh_feats_expand, self.weight, relu=True)       # hop-1 frontier embeddings (:419), [|U|, h]
+            to_feats_neigh = mask.mm(emb_u)                                      # ego-neighbor mean (:421)
             is_ab, is_norm = label == 1, label == 0
             anomaly_feat = combined[:, is_ab]
-            anomaly_feat_new = F.relu(self.fc(to_feats_neigh[is_ab]))            # outlier generation (:428-430)
+            anomaly_feat_new = ops.linear(to_feats_neigh[is_ab], self.fc.weight, relu=True)   # outlier generation (:428-430)
             combined_all = torch.cat((combined[:, is_norm], anomaly_feat_new.t()), 1)   # label-0 columns first (:450)
             anomaly_feat_new = anomaly_feat_new.t()
         return combined_all, to_feats_neigh, anomaly_feat, anomaly_feat_new
@@ -330,8 +330,8 @@ class GCN(nn.Module):
 
     def forward(self, nodes, label, train_flag):
         embeds, to_feats_neigh, anomaly_feat, anomaly_feat_new = self.enc(nodes, label, train_flag)
-        scores = self.weight.mm(embeds)
-        return scores.t(), to_feats_neigh, embeds, anomaly_feat, anomaly_feat_new
+        scores = ops.linear(embeds.t(), self.weight)                             # (weight . embeds)^T  (:174)
+        return scores, to_feats_neigh, embeds, anomaly_feat, anomaly_feat_new
 
     def to_prob(self, nodes, label):
         return torch.sigmoid(self.forward(nodes, label, train_flag=False)[0])

@@ -87,7 +87,7 @@ class GCN(nn.Module):
         squeeze = seq.dim() == 3
         x = seq[0] if squeeze else seq
         g = as_graph(adj, x.device)
-        seq_fts = self.fc(x)                                   # project first (model.py:27)
+        seq_fts = ops.linear(x, self.fc.weight)                # project first (model.py:27), tcgen05 GEMM
         if isinstance(self.act, nn.PReLU) and self.act.weight.numel() == 1:
             out = ops.gcn_aggregate(g, seq_fts, self.bias, self.act.weight)
         else:
@@ -150,7 +150,8 @@ class Model(nn.Module):
         self.disc = Discriminator(n_h, negsamp_round)
 
     def _mlp(self, t):
-        return self.fc3(self.act(self.fc2(self.act(self.fc1(t)))))
+        # f_3 = fc3(ReLU(fc2(ReLU(fc1(t)))))  (model.py:176-180), ReLU fused into the projection epilogue
+        return ops.linear(ops.linear(ops.linear(t, self.fc1.weight, relu=True), self.fc2.weight, relu=True), self.fc3.weight)
 
     def forward(self, seq1, adj, sample_abnormal_idx, normal_idx, train_flag, args, sparse=False, noise=None):
         """Returns (emb, emb_combine, f_3, emb_con, emb_abnormal) exactly like the reference.
@@ -168,7 +169,7 @@ class Model(nn.Module):
         emb_abnormal = emb_abnormal + noise
         if train_flag:
             ego = ops.spmm(g.rows(sample_abnormal_idx), emb[0])          # rows S of A_hat @ emb
-            emb_con = self.act(self.fc4(ego))
+            emb_con = ops.linear(ego, self.fc4.weight, relu=True)              # ReLU(fc4(.)), model.py:155-156
             emb_combine = torch.cat((emb[:, _device_index(normal_idx, emb.device), :], torch.unsqueeze(emb_con, 0)), 1)
             f_3 = self._mlp(emb_combine)
             emb = emb.index_copy(1, s_idx, emb_con.unsqueeze(0))         # the in-place write-back of model.py:182

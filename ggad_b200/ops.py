@@ -138,6 +138,73 @@ def _chase_stream(dev) -> torch.cuda.Stream:
     return s
 
 
+# ------------------------------------------------------------------------------------------
+# K6: dense projections (tcgen05 fp32-accurate GEMM / SIMT for tiny or unaligned shapes)
+# ------------------------------------------------------------------------------------------
+def _rowmajor(t: torch.Tensor) -> torch.Tensor:
+    """2-D fp32 CUDA view with unit inner stride and a 16-byte row pitch where possible (no copy if it already is)."""
+    if t.stride(1) == 1 and t.stride(0) >= t.shape[1] and t.data_ptr() % 4 == 0:
+        return t
+    return t.contiguous()
+
+
+def dense_matmul(a: torch.Tensor, b: torch.Tensor, *, trans_a: bool = False, trans_b: bool = False, relu: bool = False,
+                 out: Optional[torch.Tensor] = None, alpha: float = 1.0, beta: float = 0.0, path: int = 0) -> torch.Tensor:
+    """C = act(alpha * op(a) @ op(b) + beta * C) through ggad_dense_matmul (row-major fp32 CUDA matrices; see
+    include/ggad_b200.h).  The result has a leading dimension padded to a multiple of 4 floats (returned as a view),
+    so chains of projections stay on the tensor-core path."""
+    _lib.require_cuda(a, "a")
+    _lib.require_cuda(b, "b")
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.dim() == 2 and b.dim() == 2
+    a, b = _rowmajor(a), _rowmajor(b)
+    m, k = (a.shape[1], a.shape[0]) if trans_a else a.shape
+    kb, n = (b.shape[1], b.shape[0]) if trans_b else b.shape
+    if kb > k and not trans_a and trans_b:
+        raise RuntimeError(f"ggad_b200: inner dimensions differ ({k} vs {kb})")
+    k = min(k, kb)                      # operands zero-padded along k may differ in their padded extent
+    if out is None:
+        buf = torch.empty(m, _pad4(n), dtype=torch.float32, device=a.device)
+        out = buf[:, :n]
+    else:
+        assert out.shape == (m, n) and out.stride(1) == 1 and out.is_cuda and out.dtype == torch.float32
+    with torch.cuda.device(a.device):
+        check(lib().ggad_dense_matmul(int(trans_a), int(trans_b), m, n, k, ptr(a), a.stride(0), ptr(b), b.stride(0),
+                                      ptr(out), out.stride(0), float(alpha), float(beta), int(relu), int(path),
+                                      stream_ptr(a.device)))
+    return out
+
+
+class _Linear(torch.autograd.Function):
+    """y = act(x @ w^T) for a torch nn.Linear weight w [out, in] (no bias) -- model.py:27,156,176-180 and
+    src/graphsage.py:412,419,430,174.  Backward: dx = dy @ w, dw = dy^T @ x (both through ggad_dense_matmul)."""
+
+    @staticmethod
+    def forward(ctx, x, w, relu: bool):
+        k = x.shape[1]
+        xp, wp = pad_cols(x), pad_cols(w)          # inner dimension zero-padded to 16-byte rows (745 -> 748): TMA pitch
+        y = dense_matmul(xp, wp, trans_b=True, relu=relu)
+        ctx.relu, ctx.k = relu, k
+        ctx.save_for_backward(xp, wp, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xp, wp, y = ctx.saved_tensors
+        if ctx.relu:
+            dy = dy * (y > 0)
+        dx = dense_matmul(dy, wp)[:, :ctx.k] if ctx.needs_input_grad[0] else None
+        dw = dense_matmul(dy, xp, trans_a=True)[:, :ctx.k] if ctx.needs_input_grad[1] else None
+        return dx, dw, None
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, relu: bool = False) -> torch.Tensor:
+    """Drop-in for ``F.linear(x, w)`` (+ optional fused ReLU) on [..., in] inputs."""
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    y = _Linear.apply(x2, w, relu)
+    return y.reshape(*lead, w.shape[0])
+
+
 def halo_push(y: torch.Tensor, y_peers, peer_need: Optional[torch.Tensor] = None) -> None:
     """Store the rows of ``y`` [n, d] (a rank's own block of a replicated matrix) into the peers' replicas over
     NVLink: row r goes to ``y_peers[p]`` (peer-mapped device addresses of the same block) iff bit p of

@@ -183,6 +183,22 @@ GGAD_API int64_t ggad_plan_num_tiles(int64_t n_rows, int64_t nnz);
 GGAD_API int ggad_plan_build(const int64_t* rowptr, int64_t n_rows, int64_t nnz, int32_t* tile_row /*[n_tiles+1]*/,
                     int64_t* tile_edge /*[n_tiles+1]*/, ggad_stream_t stream);
 
+/* ---- K6: dense projections on the tensor cores ----------------------------------------
+ *   C[M,N] = act( alpha * op(A) * op(B) + beta * C ),  row-major fp32, act = ReLU if relu != 0
+ *   op(A) = A[M,K] (lda >= K)  or, trans_a, A stored as [K,M] (lda >= M);
+ *   op(B) = B[K,N] (ldb >= N)  or, trans_b, B stored as [N,K] (ldb >= K)  -- a torch nn.Linear weight.
+ * Replaces nn.Linear / torch.mm around the aggregation: seq_fts = X W^T (model.py:27), fc1..fc4 (model.py:156,
+ * 176-180), W . agg^T / fc(ego) / weight . emb (src/graphsage.py:412,419,430,174) and the two backward GEMMs of each
+ * (dX = dY W: no transposes; dW = dY^T X: trans_a).
+ * path 0 (auto): problems with 16-byte aligned bases / leading dimensions and enough work run on tcgen05 (operands
+ * split into three bf16 terms each on the fly, bf16 MMAs accumulated in fp32 tensor memory: ~2^-22 relative error,
+ * i.e. fp32 accuracy; plain TF32 would miss the 1e-4 parity tolerance); the rest (e.g. the h/4 -> 1 score layer,
+ * mini-batch blocks) on a register-tiled SIMT FFMA kernel.  path 1 / 2 force SIMT / tensor core (2 fails with
+ * GGAD_ERR_UNSUPPORTED if the operands do not qualify). */
+GGAD_API int ggad_dense_matmul(int32_t trans_a, int32_t trans_b, int64_t m, int64_t n, int64_t k, const float* a, int64_t lda,
+                               const float* b, int64_t ldb, float* c, int64_t ldc, float alpha, float beta, int32_t relu,
+                               int32_t path, ggad_stream_t stream);
+
 /* ---- K4: backward helper of the local-affinity cosine ---------------------------
  * de_k = ( g_k - e^_k <e^_k, g_k> ) * inv_norm_k   with e^_k = e_k * inv_norm_k, in place on g.
  * (autograd of run.py:177-180.) */

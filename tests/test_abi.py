@@ -77,6 +77,9 @@ def test_sass_is_blackwell_native(libpath):
     assert "gather_tiled_kernel" in r.stdout
     assert "UBLKCP" in r.stdout, "TMA bulk copy missing from SASS"
     assert "SYNCS" in r.stdout, "mbarrier ops missing from SASS"
+    # K6: the dense projection GEMM runs on the 5th-generation tensor cores (tcgen05.mma / tcgen05.ld / TMA tensor copies)
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
+        assert mnemonic in r.stdout, f"{mnemonic} missing from SASS (tcgen05 projection GEMM)"
 
 
 def test_product_refuses_cpu_tensors():

@@ -525,3 +525,53 @@ def test_tiled_kernel_at_c4_slice():
     table[perm.cuda()] = xp                                                        # row c of x lives at table[perm[c]]
     y2 = ops.gather_reduce(g, table, xmap=perm.to(torch.int32).cuda())["y"]
     assert torch.equal(y2, y)                                                      # same order of summation: bit-exact
+
+
+# ------------------------------------------------------------------------------------------
+# K6: dense projections (ggad_dense_matmul): tcgen05 fp32-accurate GEMM and the SIMT kernel vs fp64
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", [1, 2])
+@pytest.mark.parametrize("m,n,k", [(7535, 300, 748), (1300, 152, 300), (3000, 64, 20), (200, 64, 20), (129, 17, 65)])
+def test_dense_matmul_layouts(path, m, n, k):
+    """All three operand layouts the path uses (x W^T, dy W, dy^T x) on both code paths against fp64: rtol 1e-4 on
+    the result scale (the tensor-core path splits fp32 into three bf16 terms: ~2^-22 relative per product)."""
+    _, _, _, ops, _ = _mods()
+    aligned = k % 4 == 0 and n % 4 == 0 and m % 4 == 0
+    if path == 2 and not aligned:
+        with pytest.raises(RuntimeError):
+            ops.dense_matmul(torch.randn(m, k).cuda(), torch.randn(n, k).cuda(), trans_b=True, path=2)
+        return
+    g = torch.Generator().manual_seed(m + n + k)
+    x, w, dy = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g), torch.randn(m, n, generator=g)
+    xd, wd, dyd = x.cuda(), w.cuda(), dy.cuda()
+
+    def check(got, ref64, what):
+        scale = ref64.abs().max().item()
+        err = (got.double().cpu() - ref64).abs().max().item()
+        assert err <= 1e-4 * scale * 0.1, f"{what} m={m} n={n} k={k} path={path}: err {err:.3e} vs scale {scale:.3e}"
+
+    check(ops.dense_matmul(xd, wd, trans_b=True, path=path), x.double() @ w.double().t(), "x w^T")
+    check(ops.dense_matmul(xd, wd, trans_b=True, relu=True, path=path), torch.relu(x.double() @ w.double().t()), "relu(x w^T)")
+    check(ops.dense_matmul(dyd, wd, path=path), dy.double() @ w.double(), "dy w")
+    check(ops.dense_matmul(dyd, xd, trans_a=True, path=path), dy.double().t() @ x.double(), "dy^T x")
+    out = torch.ones(m, n, device="cuda")
+    ops.dense_matmul(xd, wd, trans_b=True, out=out, alpha=0.5, beta=2.0, path=path)
+    check(out, 0.5 * (x.double() @ w.double().t()) + 2.0, "alpha/beta")
+
+
+def test_linear_autograd_matches_torch():
+    """ops.linear (forward + both backward GEMMs, ReLU fused, inner dim 745 padded to 748) vs torch fp64 autograd."""
+    _, _, _, ops, _ = _mods()
+    torch.manual_seed(0)
+    x, w = torch.randn(2000, 745), torch.randn(300, 745) * 0.05
+    xd, wd = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    y = ops.linear(xd.unsqueeze(0), wd, relu=True)
+    assert y.shape == (1, 2000, 300)
+    gy = torch.randn(1, 2000, 300)
+    y.backward(gy.cuda())
+    x64, w64 = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    y64 = torch.relu(x64 @ w64.t())
+    y64.backward(gy[0].double())
+    for got, ref, what in ((y[0], y64, "y"), (xd.grad, x64.grad, "dx"), (wd.grad, w64.grad, "dw")):
+        err = (got.detach().double().cpu() - ref.detach()).abs().max().item()
+        assert err <= 1e-5 * ref.detach().abs().max().item(), f"{what}: {err:.3e}"

@@ -31,6 +31,7 @@ def timeit(fn, iters=10, warm=3):
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="S64")
+ap.add_argument("--no-chase", action="store_true", help="skip the chase-mode lines (variant libraries that do not flag tiles)")
 a = ap.parse_args()
 n, m, d = WORKLOADS[a.workload]
 g = synth.rmat_shard(n, m, seed=0)
@@ -57,16 +58,21 @@ some = (torch.rand(n, device="cuda") < 0.42).to(torch.int32)
 res["push variant, no row needed"] = timeit(lambda: ops.gather_reduce(g, x, y_peers=[peer.data_ptr()], peer_need=zero))
 res["push variant, 42 % of rows to one local peer"] = timeit(lambda: ops.gather_reduce(g, x, y_peers=[peer.data_ptr()], peer_need=some))
 res["push variant, every row to one local peer"] = timeit(lambda: ops.gather_reduce(g, x, y_peers=[peer.data_ptr()]))
+seven = (torch.rand(n, device="cuda") < 0.25).to(torch.int32) * 127      # N = 8 shaped: 25 % of the rows to all 7 peers
+peers7 = [peer.data_ptr()] * 7
+res["push variant, 25 % of rows to 7 local peers"] = timeit(lambda: ops.gather_reduce(g, x, y_peers=peers7, peer_need=seven))
+if a.no_chase:
+    print(f"workload {a.workload}: n={n} nnz={m} d={d}")
+    for k, v in res.items():
+        print(f"  {k:55s} {v:8.3f} ms   {m / v / 1e6:8.2f} G edges/s")
+    sys.exit(0)
 # chase mode: the gather only flags finished tiles, ggad_halo_chase (own stream, few CTAs) moves the rows
 res["chase variant, no row needed"] = timeit(lambda: ops.gather_reduce(g, x, y_peers=[peer.data_ptr()], peer_need=zero, chase=True))
 res["chase variant, 42 % of rows to one local peer"] = timeit(lambda: ops.gather_reduce(g, x, y_peers=[peer.data_ptr()], peer_need=some, chase=True))
 res["chase variant, every row to one local peer"] = timeit(lambda: ops.gather_reduce(g, x, y_peers=[peer.data_ptr()], chase=True))
-for ctas in (16, 96):
+for ctas in (24, 96):
     res[f"chase variant, 42 % of rows, {ctas} CTAs"] = timeit(
         lambda: ops.gather_reduce(g, x, y_peers=[peer.data_ptr()], peer_need=some, chase=True, chase_ctas=ctas))
-seven = (torch.rand(n, device="cuda") < 0.25).to(torch.int32) * 127      # N = 8 shaped: 25 % of the rows to all 7 peers
-peers7 = [peer.data_ptr()] * 7
-res["push variant, 25 % of rows to 7 local peers"] = timeit(lambda: ops.gather_reduce(g, x, y_peers=peers7, peer_need=seven))
 res["chase variant, 25 % of rows to 7 local peers"] = timeit(lambda: ops.gather_reduce(g, x, y_peers=peers7, peer_need=seven, chase=True))
 print(f"workload {a.workload}: n={n} nnz={m} d={d}  env: " + " ".join(k for k in ("GGAD_FORCE_FULL_EPI", "GGAD_EPI_DEFERRED", "GGAD_B200_LIB") if os.environ.get(k)))
 for k, v in res.items():
