@@ -74,6 +74,9 @@ SIGNATURES = {
     "ggad_coo_keys_to_csr": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
     "ggad_csr_transpose": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "ggad_csr_extract_rows": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "ggad_csr_row_sum_f64": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "ggad_csr_add_identity_rowptr": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "ggad_csr_scale_add_identity": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "ggad_col_histogram": (C.c_int, [_vp, _i64, _vp, _i64, _vp]),
     "ggad_block_rowptr": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp]),
     "ggad_block_fill": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp]),

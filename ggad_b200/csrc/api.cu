@@ -82,6 +82,10 @@ int rmat_keys_impl(uint64_t*, int64_t, int64_t, int32_t, int32_t, uint64_t, floa
 
 int halo_push_impl(const float*, int64_t, int64_t, int32_t, const uint32_t*, float* const*, int32_t, cudaStream_t);
 int halo_chase_impl(const ggad_chase_desc_t*, cudaStream_t);
+int csr_row_sum_f64_impl(const int64_t*, const float*, int64_t, double*, cudaStream_t);
+int csr_add_identity_rowptr_impl(const int64_t*, const int32_t*, int64_t, int64_t*, int64_t*, cudaStream_t);
+int csr_scale_add_identity_impl(const int64_t*, const int32_t*, const float*, const double*, int64_t, const int64_t*, int32_t*,
+                                float*, cudaStream_t);
 int dense_matmul_impl(int, int, int64_t, int64_t, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, float,
                       float, int, int, cudaStream_t);
 
@@ -218,6 +222,21 @@ GGAD_API int ggad_dense_matmul(int32_t trans_a, int32_t trans_b, int64_t m, int6
                                const float* b, int64_t ldb, float* c, int64_t ldc, float alpha, float beta, int32_t relu,
                                int32_t path, ggad_stream_t stream) {
   return dense_matmul_impl(trans_a, trans_b, m, n, k, a, lda, b, ldb, c, ldc, alpha, beta, relu, path, (cudaStream_t)stream);
+}
+
+GGAD_API int ggad_csr_row_sum_f64(const int64_t* rowptr, const float* val, int64_t n_rows, double* deg, ggad_stream_t stream) {
+  return csr_row_sum_f64_impl(rowptr, val, n_rows, deg, (cudaStream_t)stream);
+}
+
+GGAD_API int ggad_csr_add_identity_rowptr(const int64_t* rowptr, const int32_t* col, int64_t n, int64_t* out_rowptr,
+                                          int64_t* nnz_host, ggad_stream_t stream) {
+  return csr_add_identity_rowptr_impl(rowptr, col, n, out_rowptr, nnz_host, (cudaStream_t)stream);
+}
+
+GGAD_API int ggad_csr_scale_add_identity(const int64_t* rowptr, const int32_t* col, const float* val, const double* scale,
+                                         int64_t n, const int64_t* out_rowptr, int32_t* out_col, float* out_val,
+                                         ggad_stream_t stream) {
+  return csr_scale_add_identity_impl(rowptr, col, val, scale, n, out_rowptr, out_col, out_val, (cudaStream_t)stream);
 }
 
 GGAD_API int ggad_normalize_backward(const float* e, int64_t lde, const float* inv_norm, float* g, int64_t ldg, int64_t n_rows,

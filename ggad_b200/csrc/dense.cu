@@ -79,7 +79,10 @@ int dense_matmul_impl(int trans_a, int trans_b, int64_t M, int64_t N, int64_t K,
   GGAD_REQUIRE(path >= 0 && path <= 2, GGAD_ERR_INVALID, "dense_matmul: path must be 0 (auto), 1 (SIMT) or 2 (tensor core)");
   // tensor-core path: TMA needs 16-byte aligned bases and row pitches; it supports A[M,K] K-major with either B
   // layout, or A stored transposed ([K,M], M contiguous) with B[K,N] N-contiguous (the weight-gradient GEMM)
-  const bool aligned = aligned16(A) && aligned16(B) && aligned16(C) && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0;
+  // (pitches AND the extents of the contiguous dimensions: N for C and an N-contiguous B, K for K-contiguous
+  // operands, M for a transposed A)
+  const bool aligned = aligned16(A) && aligned16(B) && aligned16(C) && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0 &&
+                       N % 4 == 0 && (trans_a ? M % 4 == 0 : K % 4 == 0) && (trans_b ? K % 4 == 0 : true);
   const bool layout_ok = !(trans_a && trans_b);
   const bool big = M >= 64 && N >= 16 && K >= 8 && M * N * K >= (1ll << 18);
   GGAD_REQUIRE(path != 2 || (aligned && layout_ok && K > 0), GGAD_ERR_UNSUPPORTED,
@@ -94,10 +97,13 @@ int dense_matmul_impl(int trans_a, int trans_b, int64_t M, int64_t N, int64_t K,
       rc = fn(int(M), int(N), int(K), A, lda, B, ldb, C, ldc, alpha, beta, relu, ws, need, &need, st);
       GGAD_CUDA_OK(cudaFreeAsync(ws, st));
     }
-    GGAD_REQUIRE(rc == 0, GGAD_ERR_CUDA, "dense_matmul: tcgen05 GEMM failed at stage %d (%s)", -rc,
+    GGAD_REQUIRE(rc == 0 || (rc == -1 && path == 0), GGAD_ERR_CUDA, "dense_matmul: tcgen05 GEMM failed at stage %d (%s)", -rc,
                  cudaGetErrorString(cudaGetLastError()));
-    count_launch(1);
-    return GGAD_OK;
+    if (rc == 0) {
+      count_launch(1);
+      return GGAD_OK;
+    }
+    // auto mode and the tensor-core kernel declined the problem (can_implement): the SIMT kernel takes it
   }
   // SIMT: element strides of A(m,k) and B(k,n)
   const int64_t sam = trans_a ? 1 : lda, sak = trans_a ? lda : 1;

@@ -275,20 +275,21 @@ __global__ void __launch_bounds__(kThreads) gather_rows_kernel(const __grid_cons
 }
 
 // Rows [ra, rb) of the local y (finished and visible to this CTA) -> peers' replicas / multicast address.
-// peer_need (halo exchange) selects per row which peers receive it.  The rows are dealt to the lane groups round
-// robin (group g takes rows g, g + NGRP, ...; lane gl moves chunk gl of the row -- no index arithmetic beyond an add),
-// the mask is one broadcast load per row and two rows per group are in flight so the L2 re-reads overlap.
-template <int G, int CH, bool PEER>
-__device__ __forceinline__ void push_rows(const GatherArgs& a, int64_t ra, int64_t rb, int tid) {
+// peer_need (halo exchange) selects per row which peers receive it.  The masks are staged in shared memory
+// first (one coalesced load), then every thread moves two independent 16-byte chunks per iteration so the
+// L2 re-reads overlap; rows nobody needs cost one shared-memory read.
+template <bool PEER>
+__device__ __forceinline__ void push_rows(const GatherArgs& a, int64_t ra, int64_t rb, int tid, int nthreads,
+                                          uint32_t* s_need) {
   if (!PEER || a.y == nullptr || rb <= ra) return;
-  constexpr int NGRP = kThreads / G;
   const int V = a.d >> 2;
   const uint32_t all = (1u << a.n_peer) - 1u;
+  const int nrow = int(rb - ra);
   const bool mc = a.y_mc != nullptr;
-  const int g = tid / G, gl = tid % G;
-  auto need_of = [&](int64_t r) -> uint32_t {
-    return mc ? 1u : ((a.peer_need ? __ldg(a.peer_need + r) : 0xffffffffu) & all);
-  };
+  for (int j = tid; j < nrow; j += nthreads)
+    s_need[j] = mc ? 1u : ((a.peer_need ? __ldg(a.peer_need + ra + j) : 0xffffffffu) & all);
+  __syncthreads();
+  const int total = nrow * V;
   auto send = [&](int64_t off, uint32_t need, const float4& v) {
     if (mc) {
       asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.y_mc + off), "f"(v.x), "f"(v.y),
@@ -299,25 +300,19 @@ __device__ __forceinline__ void push_rows(const GatherArgs& a, int64_t ra, int64
         if ((need >> p) & 1u) stg_peer_f4(reinterpret_cast<float4*>(a.y_peer[p] + off), v);
     }
   };
-  for (int64_t r = ra + g; r < rb; r += 2 * NGRP) {
-    const int64_t r2 = r + NGRP;
-    const uint32_t n0 = need_of(r);
-    const uint32_t n1 = (r2 < rb) ? need_of(r2) : 0u;
-    if (!(n0 | n1)) continue;
-    float4 v0[CH], v1[CH];
+  for (int i0 = tid; i0 < total; i0 += 2 * nthreads) {
+    const int i1 = i0 + nthreads;
+    const int j0 = i0 / V, j1 = i1 / V;
+    const uint32_t n0 = s_need[j0];
+    const uint32_t n1 = (i1 < total) ? s_need[j1] : 0u;
+    const int64_t off0 = (ra + j0) * a.ldy + int64_t(i0 - j0 * V) * 4;
+    const int64_t off1 = (ra + j1) * a.ldy + int64_t(i1 - j1 * V) * 4;
+    float4 v0 = f4_zero(), v1 = f4_zero();
     // L2 (coherent) loads: the rows were written by this CTA a moment ago, not through the read-only path
-#pragma unroll
-    for (int j = 0; j < CH; ++j) {
-      const int ch = gl + G * j;
-      v0[j] = (n0 && ch < V) ? __ldcg(reinterpret_cast<const float4*>(a.y + r * a.ldy) + ch) : f4_zero();
-      v1[j] = (n1 && ch < V) ? __ldcg(reinterpret_cast<const float4*>(a.y + r2 * a.ldy) + ch) : f4_zero();
-    }
-#pragma unroll
-    for (int j = 0; j < CH; ++j) {
-      const int ch = gl + G * j;
-      if (n0 && ch < V) send(r * a.ldy + int64_t(ch) * 4, n0, v0[j]);
-      if (n1 && ch < V) send(r2 * a.ldy + int64_t(ch) * 4, n1, v1[j]);
-    }
+    if (n0) v0 = __ldcg(reinterpret_cast<const float4*>(a.y + off0));
+    if (n1) v1 = __ldcg(reinterpret_cast<const float4*>(a.y + off1));
+    if (n0) send(off0, n0, v0);
+    if (n1) send(off1, n1, v1);
   }
 }
 
@@ -719,7 +714,7 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
       // [r0 (+1), r1) are final" -- a release store ordered after every thread's y stores by the barrier above
       if (tid == 0) st_release_gpu(a.tile_done + k, a.tile_epoch);
     } else {
-      push_rows<G, CH, PEER>(a, r0 + ((rstart0 < 0) ? 1 : 0), r1, tid);
+      push_rows<PEER>(a, r0 + ((rstart0 < 0) ? 1 : 0), r1, tid, kThreads, reinterpret_cast<uint32_t*>(s_rend));
     }
   }
 #endif

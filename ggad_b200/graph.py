@@ -370,3 +370,56 @@ def batch_block(adj: AdjListCSR, nodes: Sequence[int], add_self: bool):
     rdeg = np.diff(rowptr)
     cdeg = np.bincount(col_local, minlength=len(frontier)).astype(np.int64)
     return dict(frontier=frontier, rowptr=rowptr, col=col_local.astype(np.int32), rdeg=rdeg, cdeg=cdeg)
+
+
+def full_batch_graphs_device(adj, device="cuda"):
+    """(A_hat, R) like ``full_batch_graphs`` but with the preprocessing ON THE DEVICE (utils.py:47-54, run.py:98-101):
+    fp64 row sums, D^-1/2, the transpose, the two fp64 products in scipy's order, "+ I" and the single rounding to
+    fp32 are CUDA kernels (ggad_csr_row_sum_f64 / ggad_csr_transpose / ggad_csr_scale_add_identity); the results are
+    bit-identical to the scipy path (tested against the reference's dense matrices).  ``adj`` is the raw adjacency as
+    a scipy matrix, or a CSRGraph already on the device whose fp32 values hold the stored weights exactly.
+
+    pow(deg, -1/2) is the one step whose last bit differs between libm and CUDA, so for integer-valued degrees (every
+    dataset of the reference) D comes from a host table indexed by the degree (max_deg + 1 numpy evaluations); for
+    non-integer degrees it is evaluated on the device and the fp32 values can differ from scipy's in the last bit."""
+    import ctypes as C
+    if isinstance(adj, CSRGraph):
+        a = adj
+    else:
+        import scipy.sparse as sp
+        m = sp.csr_matrix(adj)
+        m.sum_duplicates()
+        m.sort_indices()
+        a = CSRGraph.from_arrays(m.indptr, m.indices, m.data.astype(np.float32), m.shape[0], m.shape[1], device=device)
+    assert a.n_rows == a.n_cols, "adjacency must be square"
+    n, dev, h = a.n_rows, a.device, lib()
+    with torch.cuda.device(dev):
+        st = stream_ptr(dev)
+        deg = torch.empty(n, dtype=torch.float64, device=dev)
+        check(h.ggad_csr_row_sum_f64(ptr(a.rowptr), ptr(a.val), n, ptr(deg), st))
+        deg_i = deg.round()
+        if bool((deg_i == deg).all()) and float(deg.max()) < (1 << 24):
+            with np.errstate(divide="ignore"):
+                table = np.power(np.arange(int(deg.max().item()) + 1, dtype=np.float64), -0.5)   # utils.py:50
+            table[np.isinf(table)] = 0.0                                                         # utils.py:51
+            dis = torch.from_numpy(table).to(dev)[deg_i.long()]
+        else:
+            dis = torch.pow(deg, -0.5)
+            dis[torch.isinf(dis)] = 0.0
+        at = a.T                                         # device transpose (exact); rows keep sorted columns
+        sym = bool(torch.equal(a.rowptr, at.rowptr) and torch.equal(a.col, at.col)
+                   and (a.val is None or torch.equal(a.val, at.val)))
+
+        def plus_identity(g, scale):
+            rp = torch.empty(n + 1, dtype=torch.int64, device=dev)
+            nnz = C.c_int64(0)
+            check(h.ggad_csr_add_identity_rowptr(ptr(g.rowptr), ptr(g.col), n, ptr(rp), C.addressof(nnz), st))
+            col = torch.empty(nnz.value, dtype=torch.int32, device=dev)
+            val = torch.empty(nnz.value, dtype=torch.float32, device=dev)
+            check(h.ggad_csr_scale_add_identity(ptr(g.rowptr), ptr(g.col), ptr(g.val), ptr(scale), n, ptr(rp), ptr(col),
+                                                ptr(val), st))
+            return CSRGraph(rp, col, val, n, n, symmetric_pattern=sym)
+
+        g_hat = plus_identity(at, dis)                   # (A D)^T D + I  = D A^T D + I
+        g_r = plus_identity(a, None)                     # A + I
+    return g_hat, g_r

@@ -224,6 +224,21 @@ GGAD_API int ggad_csr_extract_rows(const int64_t* rowptr, const int32_t* col, co
 /* integer in-degree histogram of col[] (int32 counts, exact) */
 GGAD_API int ggad_col_histogram(const int32_t* col, int64_t nnz, int32_t* counts, int64_t n_cols, ggad_stream_t stream);
 
+/* ---- K7: adjacency preprocessing of program A on the device (utils.py:47-54, run.py:98-101) ----
+ * deg[r] = sum of row r in fp64 (val NULL = all ones): the `rowsum` of normalize_adj. */
+GGAD_API int ggad_csr_row_sum_f64(const int64_t* rowptr, const float* val, int64_t n_rows, double* deg, ggad_stream_t stream);
+/* "+ I" on a square CSR with sorted columns, in two steps (the result has one more entry per row without a
+ * diagonal): out_rowptr[n+1] first (*nnz_host = new nnz; synchronises), then the entries
+ *     out_val = fp32( (fp64(val) * scale[r]) * scale[c]  + [r == c] )      (scale NULL: fp32(fp64(val) + [r == c]))
+ * i.e. on CSR(A^T) with scale = deg^-1/2 this is adj = normalize_adj(A) + I, on CSR(A) without scale it is
+ * raw_adj = A + I -- same operation order and the same single rounding as scipy + the fp32 cast of run.py:106-109,
+ * so the values are bit-identical to the reference's dense tensors. */
+GGAD_API int ggad_csr_add_identity_rowptr(const int64_t* rowptr, const int32_t* col, int64_t n, int64_t* out_rowptr,
+                                          int64_t* nnz_host, ggad_stream_t stream);
+GGAD_API int ggad_csr_scale_add_identity(const int64_t* rowptr, const int32_t* col, const float* val, const double* scale,
+                                         int64_t n, const int64_t* out_rowptr, int32_t* out_col, float* out_val,
+                                         ggad_stream_t stream);
+
 /* ---- K7: mini-batch frontier on the device --------------------------------------------------
  * Replaces the Python set unions of GCNAggregator / MeanAggregator (src/graphsage.py:305-311,335-341,
  * 82-88).  adj_rowptr/adj_col is the device CSR of the adjacency lists (neighbor ids sorted, as built

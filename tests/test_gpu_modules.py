@@ -6,6 +6,8 @@ import numpy as np
 import pytest
 import torch
 
+import scipy.sparse as sp
+
 import oracle
 from helpers import assert_close, case_adj_lists, case_adjacency, golden_cases, load_case
 
@@ -267,3 +269,35 @@ def test_on_device_auroc_matches_sklearn():
     auc = float(metrics.roc_auc(torch.from_numpy(s).cuda(), torch.from_numpy(y).cuda()))
     ap = float(metrics.average_precision(torch.from_numpy(s).cuda(), torch.from_numpy(y).cuda()))
     assert abs(auc - roc_auc_score(y, s)) < 1e-9 and abs(ap - average_precision_score(y, s)) < 1e-9
+
+
+@pytest.mark.parametrize("name", golden_cases("fb_"))
+def test_device_normalize_adj_bit_exact(name):
+    """f4: normalize_adj + I and raw_adj = A + I built by the device kernels equal the reference's dense fp32
+    matrices BIT FOR BIT (golden ``adj_hat_dense`` from run.py:96-109), and the scipy host path entry for entry."""
+    from ggad_b200 import graph
+    c = load_case(name)
+    a = case_adjacency(c)
+    g_hat, g_r = graph.full_batch_graphs_device(a)
+    assert np.array_equal(g_hat.to_scipy().toarray().astype(np.float32), c["out"]["adj_hat_dense"])
+    h_hat, h_r = graph.full_batch_graphs(a)
+    for dv, hs in ((g_hat, h_hat), (g_r, h_r)):
+        assert torch.equal(dv.rowptr, hs.rowptr) and torch.equal(dv.col, hs.col) and torch.equal(dv.val, hs.val)
+        assert dv.symmetric_pattern == hs.symmetric_pattern
+    n = a.shape[0]
+    assert np.array_equal(g_r.to_scipy().toarray(), (a + sp.eye(n)).toarray().astype(np.float32))
+
+
+def test_device_normalize_adj_config_shape():
+    """Same at the Amazon shape (C2: 11 944 nodes / 4.4 M entries), weighted and asymmetric on top: every stored value
+    of the device-built A_hat equals the scipy fp64 -> fp32 result."""
+    from ggad_b200 import graph
+    rng = np.random.default_rng(5)
+    n, m = 11944, 2_200_000
+    a = sp.coo_matrix((rng.integers(1, 4, m).astype(np.float64), (rng.integers(0, n, m), rng.integers(0, n, m))), shape=(n, n)).tocsr()
+    g_hat, g_r = graph.full_batch_graphs_device(a)
+    ref = (oracle.normalize_adj(a) + sp.eye(n)).tocsr()
+    ref.sort_indices()
+    assert np.array_equal(g_hat.rowptr.cpu().numpy(), ref.indptr) and np.array_equal(g_hat.col.cpu().numpy(), ref.indices)
+    assert np.array_equal(g_hat.val.cpu().numpy(), ref.data.astype(np.float32))
+    assert not g_hat.symmetric_pattern

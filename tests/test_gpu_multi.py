@@ -74,6 +74,20 @@ def _worker(rank, world, port, q):
     halo_ok = halo_ok and torch.equal(dx_halo, dx[lo:hi])
     frac = float((need != 0).float().mean())
     rep.barrier(1)
+    # chase exchange (tile-done flags + ggad_halo_chase on a second stream), plain and with the hybrid rule "rows that
+    # >= 1 peer needs go once through the multicast address": same contract as the halo push above
+    for mc_min in ([0, 1] if rep.multicast_ptr else [0]):
+        rep.barrier(0)
+        rep.buf.fill_(float("nan"))
+        rep.barrier(1)
+        ops.gather_reduce(fwd, x, y_out=rep.local_rows, y_peers=rep.peer_row_ptrs, peer_need=need, chase=True,
+                          y_multicast=rep.multicast_row_ptr if mc_min else None, mc_min_peers=mc_min)
+        rep.barrier(0)
+        chase_ok = torch.equal(rep.buf[mine], y[mine])
+        if not mc_min:
+            chase_ok = chase_ok and bool(torch.isnan(rep.buf[~mine]).all())
+        halo_ok = halo_ok and chase_ok and torch.equal(ops.gather_reduce(bwd, rep.buf)["y"], dx[lo:hi])
+        rep.barrier(1)
     # input-side halo (ggad_halo_push): each rank holds only its own block of X plus the rows its forward shard
     # gathers, pushed by their owners; the forward on that replica is bit-identical
     x_rep = gdist.PeerReplica(n_glob, d, fr, rank, dev)
@@ -107,6 +121,17 @@ def _worker(rank, world, port, q):
         dx_ref = ops.gather_reduce(full.T, y_ref)["y"]
         ok = ok and torch.allclose(y, y_ref, rtol=1e-5, atol=1e-6) and torch.allclose(dx, dx_ref, rtol=1e-5, atol=1e-5)
         msg += f"max|dy|={float((y - y_ref).abs().max()):.3e} max|ddx|={float((dx - dx_ref).abs().max()):.3e}"
+        # ... and against the ORACLE (scipy CSR in fp64), not only against the same kernels on one GPU
+        import scipy.sparse as sp
+        a64 = sp.csr_matrix((np.ones(full.nnz), full.col.cpu().numpy(), full.rowptr.cpu().numpy()), shape=(n_glob, n_glob))
+        a64 = sp.diags(full.row_scale.double().cpu().numpy()) @ a64
+        y64 = a64 @ x.double().cpu().numpy()
+        dx64 = a64.T @ y64
+        for got, ref, mag, what in ((y, y64, abs(a64) @ np.abs(x.double().cpu().numpy()), "y"),
+                                    (dx, dx64, abs(a64.T) @ np.abs(y64), "dx")):
+            worst = float((np.abs(got.double().cpu().numpy() - ref) / (1e-4 * np.abs(ref) + 1e-5 * mag + 1e-30)).max())
+            ok = ok and worst <= 1.0
+            msg += f" oracle {what} err/bound={worst:.3f}"
         # exact integer check: the transposed shards tile the global transpose
         assert int(bwd.nnz) > 0
     tot = torch.tensor([bwd.nnz], device=dev)
