@@ -819,7 +819,7 @@ def main():
                     help="exchange=chase: rows needed by at least this many peers go once through the NVSwitch multicast "
                          "address instead of one unicast store per peer (0 = never)")
     ap.add_argument("--verify-rows", type=int, default=4096, help="rows of Y and of dX recomputed on the CPU after the timed region")
-    ap.add_argument("--exchange", default="chase", choices=["chase", "halo", "fused", "multicast", "nccl"],
+    ap.add_argument("--exchange", default="halo", choices=["chase", "halo", "fused", "multicast", "nccl"],
                     help="N>1: how the forward output reaches the ranks that gather it next.  chase = the gather kernel "
                          "flags finished tiles and a concurrent kernel on a few SMs stores the halo rows over NVLink; "
                          "halo = NVLink P2P stores "
