@@ -81,8 +81,6 @@ def main():
             t[0] = tm[0]
         return float(t[0]), float(t[1]), float(loss), dict(model.stats)
 
-    rng = np.random.default_rng(7)
-
     if args.mode in ("sharded", "both"):
         t0 = time.perf_counter()
         # A[:, lo:hi]: regenerate every destination shard's edges, keep sources in this rank's range, transpose
@@ -120,9 +118,10 @@ def main():
         model = sharded.ShardedTwoLayerSage(sharded.DeviceBackend(adj), x_full, 0, n_glob, *ws)
         model.world = 1                        # no data-path collective: every rank owns everything
         build_s = time.perf_counter() - t0
+        own = np.random.default_rng(100 + rank)
 
         def seed_fn(i):                        # every rank draws its OWN seeds
-            s = torch.from_numpy(rng.integers(0, n_glob, args.seeds) if rank == 0 else np.random.default_rng(100 + rank + 1000 * i).integers(0, n_glob, args.seeds))
+            s = torch.from_numpy(own.integers(0, n_glob, args.seeds))
             return s, (s % 2)
 
         def sync(m):
