@@ -39,6 +39,9 @@ WORKLOADS = {
     "C3": (39_357, 21_222_543, 300),            # T-Finance-shaped layer-2 pass (L2-resident table)
     "C2": (11_944, 4_398_392, 300),             # Amazon-shaped layer-2 pass
     "tiny": (50_000, 1_000_000, 64),
+    # program B's training batch on the DGraph-shaped graph (BASELINE.json config 4): metric = mini-batches/s,
+    # replicated graph + table, every rank its own seed batches (tools/bench_minibatch.py does the work)
+    "C4mb": (3_700_550, 36_552_754, 17),
 }
 RMAT = (0.57, 0.19, 0.19)
 
@@ -638,7 +641,7 @@ def _e2e_leg(args, world, rank, dev, fwd, bwd, fr, br, value, rep=None, need_y=N
         ra, rt = res(fwd), res(bwd)
         # two pipeline slots (own stream + device scratch + pinned result buffers): the H2D of step i+1 overlaps
         # the D2H of step i; every step still copies its features in and its gradient + loss out
-        n_slots = 2
+        n_slots = args.e2e_slots
         slots = []
         for _ in range(n_slots):
             slots.append(dict(stream=torch.cuda.Stream(device=dev),
@@ -653,7 +656,17 @@ def _e2e_leg(args, world, rank, dev, fwd, bwd, fr, br, value, rep=None, need_y=N
             _lib.check(lib.ggad_spmm_fwd_bwd_host_enqueue(C.byref(ra), C.byref(rt), ptr(x_host), None, ptr(s["dx"]),
                                                           ptr(s["loss"]), d, ptr(s["bufs"][0]), ptr(s["bufs"][1]),
                                                           ptr(s["bufs"][2]), ptr(s["ws"]), s["stream"].cuda_stream))
-        for i in range(2):                      # warm-up
+        # the host link on its own (one direction at a time), so the bound of the end-to-end figure is stated
+        link = {}
+        for tag, dst, src in (("h2d", slots[0]["bufs"][0], x_host), ("d2h", slots[0]["dx"], slots[0]["bufs"][2])):
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            link[tag + "_GBs_alone"] = round(3 * src.numel() * 4 / (time.perf_counter() - t0) / 1e9, 1)
+        for i in range(n_slots):                # warm-up
             enqueue(i)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -662,7 +675,7 @@ def _e2e_leg(args, world, rank, dev, fwd, bwd, fr, br, value, rep=None, need_y=N
         torch.cuda.synchronize()
         times = [(time.perf_counter() - t0) / steps]
         assert all(float(s["loss"][0]) > 0 for s in slots)
-        api = "ggad_spmm_fwd_bwd_host_enqueue (C ABI, pinned host buffers, 2 pipelined streams)"
+        api = f"ggad_spmm_fwd_bwd_host_enqueue (C ABI, pinned host buffers, {n_slots} pipelined streams)"
     elif rep is not None:
         # N > 1, halo exchange end to end: every step copies the rank's feature shard in from pinned host memory,
         # pushes the rows its peers' forward shards gather (ggad_halo_push), runs the fused forward (+ halo push of
@@ -747,8 +760,12 @@ def _e2e_leg(args, world, rank, dev, fwd, bwd, fr, br, value, rep=None, need_y=N
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     sec = float(t.item())
-    return {"value": args.edges * world / sec, "unit": "edges/s", "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": int(d2h), "ms_per_step": sec * 1e3, "steps": steps, "api": api}
+    res = {"value": args.edges * world / sec, "unit": "edges/s", "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "ms_per_step": sec * 1e3, "steps": steps, "api": api,
+           "host_link_GBs_achieved": round((h2d + d2h) / sec / 1e9, 1)}
+    if world == 1:
+        res["host_link"] = link
+    return res
 
 
 def reference(args):
@@ -773,6 +790,37 @@ def reference(args):
         "e2e": {"value": cpu["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(out)
+
+
+def minibatch_workload(args):
+    """--workload C4mb: one step = one training batch of program B (150 + 50 nodes: device frontier, two gathers,
+    dense tail, backward, Adam; src/model_handler.py:330-364) on the DGraph-shaped synthetic graph; N ranks = data
+    parallel replicas with their own seed batches.  Re-emits tools/bench_minibatch.py's result in the bench contract."""
+    import io
+    import contextlib
+    import runpy
+    rank = int(os.environ.get("RANK", "0"))
+    argv = ["bench_minibatch.py", "--nodes", str(args.nodes), "--edges", str(args.edges), "--d", str(args.width),
+            "--iters", str(max(10, args.steps)), "--warm", str(max(3, args.warmup))]
+    argv += ["--cpu-nodes", "0"] if (args.no_cpu or args.impl != "reference") else []
+    old = sys.argv
+    sys.argv = argv
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            runpy.run_path(os.path.join(ROOT, "tools", "bench_minibatch.py"), run_name="__main__")
+    finally:
+        sys.argv = old
+    if rank != 0:
+        return
+    r = json.loads(buf.getvalue().strip().splitlines()[-1])
+    emit({"metric": "mini-batches/sec (GGAD GraphSAGE training batch, 150 + 50 nodes)", "value": r["batches_per_s"],
+          "unit": "batches/s", "n_gpus": r["n_gpus"], "steps": max(10, args.steps), "warmup": max(3, args.warmup),
+          "ms_per_step": r["wall_ms_per_lockstep_batch"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+          "dtype": "f32", "data": "synthetic (DGraph-shaped R-MAT, on-device)",
+          "config": {"workload": "C4mb", "nodes": r["nodes"], "adjacency_entries": r["adjacency_entries"], "width": r["d"],
+                     "h": r["h"], "batch": r["batch"], "parallelism": f"data parallel x{r['n_gpus']} (replicated graph + table)"},
+          "detail": r, "gpu_launches": int(r["ggad_launches_per_batch"] * max(10, args.steps))})
 
 
 _RESULT_FD = None
@@ -831,6 +879,7 @@ def main():
     ap.add_argument("--peer-debug", default=None, choices=["zero_mask", "local_peers"],
                     help="diagnostics only (results are NOT exchanged): isolate the cost of the peer stores")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-slots", type=int, default=3, help="N=1 end-to-end leg: pipeline depth (streams with their own scratch)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.workload != "custom":
@@ -838,6 +887,8 @@ def main():
         args.nodes = args.nodes or n
         args.edges = args.edges or m
         args.width = args.width or d
+    if args.workload == "C4mb":
+        return minibatch_workload(args)
     if args.impl == "reference":
         args.cpu_frac = args.cpu_frac or 1
         reference(args)

@@ -41,6 +41,9 @@ def main():
                          "many edges (a new maximum later costs a cudaMalloc, ~1.5 s when the memory is peer-mapped on an "
                          "8-GPU box).  -1 = twice the largest block of the warm-up batches, 0 = no hint")
     ap.add_argument("--diag", action="store_true", help="also time the rank-local part of every batch (adds a sync)")
+    ap.add_argument("--phases", action="store_true",
+                    help="wrap the phases of a batch (hop blocks, gathers, dense tail, backward, optimiser) with "
+                         "synchronising timers and report their mean ms (perturbs the total; diagnosis only)")
     args = ap.parse_args()
     from ggad_b200 import _lib, graphsage as gs, synth
     from ggad_b200.train import DataParallelMiniBatch
@@ -87,6 +90,29 @@ def main():
         return dp.step(nodes, labels)[0]
 
     local_ms = []
+    phase_ms = {}
+    if args.phases:
+        import functools
+
+        def wrap(mod, name, label):
+            fn = getattr(mod, name)
+
+            @functools.wraps(fn)
+            def timed(*a, **k):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                r = fn(*a, **k)
+                torch.cuda.synchronize()
+                phase_ms.setdefault(label, []).append((time.perf_counter() - t0) * 1e3)
+                return r
+            setattr(mod, name, timed)
+        wrap(gs, "_block_for", "hop block (frontier + block CSR)")
+        wrap(gs, "_aggregate", "gather-reduce from the table")
+        wrap(agg, "forward", "aggregator.forward (2 blocks + 2 gathers)")
+        wrap(enc, "forward", "encoder.forward (aggregator + projections + ego)")
+        wrap(model, "loss", "model.loss (forward)")
+        wrap(torch.Tensor, "backward", "backward")
+        wrap(opt, "step", "optimizer.step")
 
     stats = []
     for i in range(args.iters + args.warm):
@@ -129,6 +155,8 @@ def main():
            "mean_frontier_U2": float(np.mean(st[:, 4])), "mean_hop2_edges": float(np.mean(st[:, 5])),
            "edges_per_s": edges * agg_bps, "loss": lv,
            "reference_cpu_s_per_batch_300k_proxy_survey": 1.52}
+    if args.phases:
+        out["phase_ms_mean"] = {k: round(float(np.mean(v[-3 * args.iters // 4:])) * (len(v) / (args.iters + args.warm)), 3) for k, v in phase_ms.items()}
     if args.diag:
         per = {"rank": rank, "local_ms": [round(float(np.percentile(local_ms[args.warm:], q)), 2) for q in (10, 50, 90, 100)],
                "step_ms": [round(float(np.percentile(st[:, 0], q)), 2) for q in (10, 50, 90, 100)]}
