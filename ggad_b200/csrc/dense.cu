@@ -4,6 +4,8 @@
 //                                    -> a plain register-tiled SIMT FFMA kernel (exact fp32)
 // Roofline: tensor-bound for the full-batch layers (C1 layer 1: 7535 x 745 x 300 = 3.4 GFLOP), latency-bound
 // for the mini-batch blocks.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ggad {
@@ -18,26 +20,39 @@ int fast_f32_nt(int, int, int, const float*, int64_t, const float*, int64_t, flo
 // C[m,n] = act(alpha * sum_k A(m,k) B(k,n) + beta * C[m,n]) with arbitrary element strides:
 // A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn].  64 x 64 tile, 16-deep k slices, 4 x 4 per thread.
 constexpr int kBM = 64, kBN = 64, kBK = 16;
+// Split-K (weight gradients: K = number of nodes, M x N = a few tiles): blockIdx.z owns the k range
+// [z * k_chunk, (z+1) * k_chunk) and writes its partial tile to part[z][M][N]; splitk_reduce_kernel sums the slices
+// in a fixed order (deterministic) and applies alpha / beta / ReLU.
 __global__ void __launch_bounds__(256) dense_simt_kernel(int M, int N, int K, const float* __restrict__ A, int64_t sam, int64_t sak,
                                                          const float* __restrict__ B, int64_t sbk, int64_t sbn,
-                                                         float* __restrict__ C, int64_t ldc, float alpha, float beta, int relu) {
+                                                         float* __restrict__ C, int64_t ldc, float alpha, float beta, int relu,
+                                                         int k_chunk, float* __restrict__ part) {
   __shared__ float sA[kBK][kBM + 4];
   __shared__ float sB[kBK][kBN + 4];
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
   const int tm = (tid / 16) * 4, tn = (tid % 16) * 4;
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += kBK) {
+  const int k_lo = part ? blockIdx.z * k_chunk : 0;
+  const int k_hi = part ? ((k_lo + k_chunk < K) ? k_lo + k_chunk : K) : K;
+  if (part) {
+    C = part + int64_t(blockIdx.z) * M * N;
+    ldc = N;
+    alpha = 1.f;
+    beta = 0.f;
+    relu = 0;
+  }
+  for (int k0 = k_lo; k0 < k_hi; k0 += kBK) {
     for (int i = tid; i < kBM * kBK; i += 256) {
       // consecutive threads walk the contiguous direction of each operand
       const int mm = (sak == 1) ? i / kBK : i % kBM, kk = (sak == 1) ? i % kBK : i / kBM;
       const int gm = m0 + mm, gk = k0 + kk;
-      sA[kk][mm] = (gm < M && gk < K) ? __ldg(A + gm * sam + gk * sak) : 0.f;
+      sA[kk][mm] = (gm < M && gk < k_hi) ? __ldg(A + gm * sam + gk * sak) : 0.f;
     }
     for (int i = tid; i < kBN * kBK; i += 256) {
       const int nn = (sbk == 1) ? i / kBK : i % kBN, kk = (sbk == 1) ? i % kBK : i / kBN;
       const int gn = n0 + nn, gk = k0 + kk;
-      sB[kk][nn] = (gn < N && gk < K) ? __ldg(B + gk * sbk + gn * sbn) : 0.f;
+      sB[kk][nn] = (gn < N && gk < k_hi) ? __ldg(B + gk * sbk + gn * sbn) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -68,6 +83,21 @@ __global__ void __launch_bounds__(256) dense_simt_kernel(int M, int N, int K, co
   }
 }
 
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N, float* __restrict__ C, int64_t ldc,
+                                     float alpha, float beta, int relu) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= int64_t(M) * N) return;
+  float v = 0.f;
+  for (int z = 0; z < splits; ++z) v += part[int64_t(z) * M * N + i];
+  const int m = int(i / N), n = int(i % N);
+  v *= alpha;
+  if (beta != 0.f) v = fmaf(beta, C[m * ldc + n], v);
+  if (relu) v = fmaxf(v, 0.f);
+  C[m * ldc + n] = v;
+}
+
+int sm_count_cached();
+
 int dense_matmul_impl(int trans_a, int trans_b, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
                       int64_t ldb, float* C, int64_t ldc, float alpha, float beta, int relu, int path, cudaStream_t st) {
   GGAD_REQUIRE(M >= 0 && N >= 0 && K >= 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), GGAD_ERR_INVALID,
@@ -84,7 +114,11 @@ int dense_matmul_impl(int trans_a, int trans_b, int64_t M, int64_t N, int64_t K,
   const bool aligned = aligned16(A) && aligned16(B) && aligned16(C) && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0 &&
                        N % 4 == 0 && (trans_a ? M % 4 == 0 : K % 4 == 0) && (trans_b ? K % 4 == 0 : true);
   const bool layout_ok = !(trans_a && trans_b);
-  const bool big = M >= 64 && N >= 16 && K >= 8 && M * N * K >= (1ll << 18);
+  // few output tiles and a long k loop (dW = dY^T X: K = number of nodes) would leave most SMs idle: those go to the
+  // split-K SIMT path below
+  const int64_t tc_tiles = ((M + 127) / 128) * ((N + 127) / 128);
+  const bool skinny = tc_tiles < 48 && K >= 4096 && !(trans_a && !getenv("GGAD_DENSE_NO_STREAMK"));   // A^T B runs stream-K
+  const bool big = M >= 64 && N >= 16 && K >= 8 && M * N * K >= (1ll << 18) && !skinny;
   GGAD_REQUIRE(path != 2 || (aligned && layout_ok && K > 0), GGAD_ERR_UNSUPPORTED,
                "dense_matmul: the tensor-core path needs 16-byte aligned operands and not both operands transposed");
   if (K > 0 && aligned && layout_ok && (path == 2 || (path == 0 && big))) {
@@ -110,7 +144,30 @@ int dense_matmul_impl(int trans_a, int trans_b, int64_t M, int64_t N, int64_t K,
   const int64_t sbk = trans_b ? 1 : ldb, sbn = trans_b ? ldb : 1;
   dim3 grid((unsigned)((N + kBN - 1) / kBN), (unsigned)((M + kBM - 1) / kBM));
   GGAD_REQUIRE(grid.y <= 65535, GGAD_ERR_UNSUPPORTED, "dense_matmul: M too large for the SIMT path");
-  dense_simt_kernel<<<grid, 256, 0, st>>>(int(M), int(N), int(K), A, sam, sak, B, sbk, sbn, C, ldc, alpha, beta, relu);
+  const int64_t tiles = int64_t(grid.x) * grid.y;
+  const int sms = sm_count_cached();
+  int splits = 1;
+  if (sms > 0 && tiles < 2 * sms && K >= 2048) {
+    splits = int((3ll * sms + tiles - 1) / tiles);                 // ~3 CTAs per SM in total
+    if (splits > K / 256) splits = int(K / 256);
+    if (splits > 256) splits = 256;
+  }
+  if (splits > 1) {
+    int k_chunk = int((K + splits - 1) / splits);
+    k_chunk = (k_chunk + kBK - 1) / kBK * kBK;
+    splits = int((K + k_chunk - 1) / k_chunk);
+    float* part = nullptr;
+    GGAD_CUDA_OK(temp_alloc(reinterpret_cast<void**>(&part), size_t(splits) * M * N * 4, st));
+    grid.z = splits;
+    dense_simt_kernel<<<grid, 256, 0, st>>>(int(M), int(N), int(K), A, sam, sak, B, sbk, sbn, C, ldc, alpha, beta, relu, k_chunk, part);
+    GGAD_CUDA_OK(cudaGetLastError());
+    splitk_reduce_kernel<<<(unsigned)((M * N + 255) / 256), 256, 0, st>>>(part, splits, int(M), int(N), C, ldc, alpha, beta, relu);
+    GGAD_CUDA_OK(cudaGetLastError());
+    GGAD_CUDA_OK(cudaFreeAsync(part, st));
+    count_launch(2);
+    return GGAD_OK;
+  }
+  dense_simt_kernel<<<grid, 256, 0, st>>>(int(M), int(N), int(K), A, sam, sak, B, sbk, sbn, C, ldc, alpha, beta, relu, 0, nullptr);
   GGAD_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return GGAD_OK;

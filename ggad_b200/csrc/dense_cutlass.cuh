@@ -19,6 +19,8 @@
 #include "cutlass/epilogue/fusion/operations.hpp"
 #include "cutlass/epilogue/thread/activation.h"
 #include "cutlass/gemm/kernel/gemm_universal.hpp"
+#include "cutlass/gemm/kernel/tile_scheduler.hpp"
+#include "cutlass/kernel_hardware_info.hpp"
 #include "cutlass/gemm/device/gemm_universal_adapter.h"
 #include "cutlass/util/packed_stride.hpp"
 
@@ -26,7 +28,9 @@ namespace ggad {
 
 // C[M,N] = act(alpha * A[M,K] * B[K,N] + beta * C).  LayoutA / LayoutB are the CUTLASS tags of the GEMM operands:
 // A RowMajor = K contiguous, B ColumnMajor = K contiguous (a row-major [N,K] weight), B RowMajor = N contiguous.
-template <class LayoutA, class LayoutB, bool RELU>
+// STREAMK: the stream-K tile scheduler splits the k loop of the few output tiles of a weight-gradient GEMM
+// (dW = dY^T X: K = number of nodes, M x N = 300 x 300) over all SMs, with a deterministic fix-up through a workspace.
+template <class LayoutA, class LayoutB, bool RELU, bool STREAMK = false>
 struct FastF32Gemm {
   using ArchTag = cutlass::arch::Sm100;
   using OpClass = cutlass::arch::OpClassTensorOp;
@@ -43,15 +47,16 @@ struct FastF32Gemm {
       ArchTag, OpClass, float, LayoutA, kAlign, float, LayoutB, kAlign, float, TileShape, ClusterShape,
       cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename CollectiveEpilogue::SharedStorage))>,
       cutlass::gemm::KernelTmaWarpSpecialized1SmFastFP32Sm100>::CollectiveOp;
-  using GemmKernel = cutlass::gemm::kernel::GemmUniversal<cute::Shape<int, int, int, int>, CollectiveMainloop, CollectiveEpilogue, void>;
+  using Scheduler = std::conditional_t<STREAMK, cutlass::gemm::StreamKScheduler, void>;
+  using GemmKernel = cutlass::gemm::kernel::GemmUniversal<cute::Shape<int, int, int, int>, CollectiveMainloop, CollectiveEpilogue, Scheduler>;
   using Gemm = cutlass::gemm::device::GemmUniversalAdapter<GemmKernel>;
 };
 
 // returns 0, or a negative stage code (1 can_implement, 2 workspace, 3 initialize, 4 run) for the caller to report
-template <class LayoutA, class LayoutB, bool RELU>
+template <class LayoutA, class LayoutB, bool RELU, bool STREAMK = false>
 int run_fast_f32(int M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
                  float alpha, float beta, void* ws, size_t ws_bytes, size_t* ws_needed, cudaStream_t st) {
-  using G = typename FastF32Gemm<LayoutA, LayoutB, RELU>::Gemm;
+  using G = typename FastF32Gemm<LayoutA, LayoutB, RELU, STREAMK>::Gemm;
   using StrideA = typename G::GemmKernel::StrideA;
   using StrideB = typename G::GemmKernel::StrideB;
   using StrideC = typename G::GemmKernel::StrideC;
@@ -65,6 +70,10 @@ int run_fast_f32(int M, int N, int K, const float* A, int64_t lda, const float* 
   typename G::Arguments args{cutlass::gemm::GemmUniversalMode::kGemm, {M, N, K, 1}, {A, sa, B, sb}, {{}, C, sc, C, sc}};
   args.epilogue.thread.alpha = alpha;
   args.epilogue.thread.beta = beta;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  args.hw_info.device_id = dev;
+  args.hw_info.sm_count = cutlass::KernelHardwareInfo::query_device_multiprocessor_count(dev);
   G gemm;
   if (gemm.can_implement(args) != cutlass::Status::kSuccess) return -1;
   const size_t need = G::get_workspace_size(args);

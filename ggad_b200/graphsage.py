@@ -265,16 +265,74 @@ class GCNAggregator(nn.Module):
 
     def forward(self, nodes, to_neighs, adj_list, train_flag):
         device = _device_of(self.features)
-        hop1 = _block_for(nodes, to_neighs, adj_list, True, device)             # N(b) U {b}   (:305)
+        ready = self.prefetcher.take(nodes) if (getattr(self, "prefetcher", None) is not None and train_flag == True) else None
+        hop1 = ready[0] if ready else _block_for(nodes, to_neighs, adj_list, True, device)    # N(b) U {b}   (:305)
         to_feats = _aggregate(hop1, "sym", self.features, device)
         to_feats_neigh = None
         if train_flag == True:
-            hop2 = _block_for(hop1.frontier_d, None, adj_list, False, device)        # no self union (:335)
+            hop2 = ready[1] if ready else _block_for(hop1.frontier_d, None, adj_list, False, device)   # no self union (:335)
             to_feats_neigh = _aggregate(hop2, "sym", self.features, device)
             self.last_blocks = (hop1, hop2)
         else:
             self.last_blocks = (hop1, None)
         return to_feats, to_feats_neigh, BlockMask(hop1)
+
+
+class BlockPrefetcher:
+    """Input pipeline of program B's training loop: the two hop blocks of the NEXT batch (frontier union, block CSR,
+    batch-local degrees -- integer work that ends in two device->host size reads per hop) are built by a helper thread
+    on its own CUDA stream while the current batch runs its gathers, dense tail, backward and optimiser step.
+    The reference builds them with Python set unions inside ``GCNAggregator.forward`` (src/graphsage.py:305-311,
+    335-341); results are identical (same kernels), only the schedule changes.
+
+        pf = BlockPrefetcher(aggregator, adj_lists);  pf.submit(batch_0)
+        for i: pf.submit(batch_{i+1});  model.loss(batch_i, labels_i) ...     # forward picks the prepared blocks up
+    """
+
+    def __init__(self, aggregator: "GCNAggregator", adj_lists):
+        import threading
+        self.agg, self.adj_lists = aggregator, adj_lists
+        self.device = _device_of(aggregator.features)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.pending = {}
+        self.lock = threading.Lock()
+        aggregator.prefetcher = self
+
+    def _build(self, nodes, slot):
+        try:
+            with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+                hop1 = _block_for(nodes, None, self.adj_lists, True, self.device)
+                hop2 = _block_for(hop1.frontier_d, None, self.adj_lists, False, self.device)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+            slot["result"] = (hop1, hop2, ev)
+        except BaseException as e:           # surfaced by take()
+            slot["error"] = e
+
+    def submit(self, nodes) -> None:
+        import threading
+        slot = {}
+        slot["thread"] = threading.Thread(target=self._build, args=(nodes, slot), daemon=True)
+        with self.lock:
+            self.pending[id(nodes)] = (nodes, slot)
+        slot["thread"].start()
+
+    def take(self, nodes):
+        with self.lock:
+            hit = self.pending.pop(id(nodes), None)
+        if hit is None or hit[0] is not nodes:
+            return None
+        slot = hit[1]
+        slot["thread"].join()
+        if "error" in slot:
+            raise slot["error"]
+        hop1, hop2, ev = slot["result"]
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for b in (hop1, hop2):               # allocated on the helper stream, consumed on this one
+            for t in (b.rowptr_d, b.col_d, b.frontier_d, b.cdeg_i, b.rdeg_i, b.rdeg_d, b.cdeg_d):
+                t.record_stream(cur)
+        return hop1, hop2
 
 
 class GCNEncoder(nn.Module):
@@ -355,6 +413,41 @@ class GCN(nn.Module):
         return (1 - (aff_normal - aff_abnormal)).clamp_min(min=0)                # margin 1 (:236-240)
 
     def loss(self, nodes, labels):
+        """total, cls, margin, rec of src/graphsage.py:244-258 -- same numbers as composing forward / affinity / recon2
+        (``loss_reference_path`` below, kept for the parity test), but written with label MASKS and one stable sort
+        instead of boolean indexing: every tensor has a static shape, so the step issues no device->host reads after
+        the frontier is built (boolean indexing synchronises five times per batch)."""
+        enc = self.enc
+        lab = labels.detach()
+        if not lab.is_cuda:
+            if bool(((lab != 0) & (lab != 1)).any()):           # CPU labels: free to inspect
+                return self.loss_reference_path(nodes, labels)
+        neigh_feats, neigh_feats_expand, mask = enc.aggregator.forward(nodes, _LazyNeighs(enc.adj_lists, nodes),
+                                                                       enc.adj_lists, True)
+        dev = neigh_feats.device
+        lab = lab.to(dev).reshape(-1)
+        is_ab = lab == 1
+        m1 = is_ab.to(torch.float32)
+        m0 = (lab == 0).to(torch.float32)
+        combined = ops.linear(neigh_feats, enc.weight, relu=True)                # [B,h]  (:412)
+        emb_u = ops.linear(neigh_feats_expand, enc.weight, relu=True)            # [|U|,h] (:419)
+        ego = mask.mm(emb_u)                                                     # [B,h]  (:421)
+        afn_all = ops.linear(ego, enc.fc.weight, relu=True)                      # ReLU(fc(ego)) for every row; rows with label 1 are consumed (:430)
+        # combined_all (:450): label-0 columns in batch order, then the generated outliers -> stable sort of the labels
+        order = torch.sort(is_ab.to(torch.int8), stable=True).indices
+        rows_all = torch.where(is_ab[order].unsqueeze(1), afn_all[order], combined[order])   # combined_all^T, [B,h]
+        scores = ops.linear(rows_all, self.weight)                               # (:174)
+        loss_cls = torch.mean(self.xent(scores.squeeze(), lab.to(torch.float32)))   # labels stay in batch order (:246)
+        aff = torch.cosine_similarity(rows_all, ego, dim=1)                      # column p against ego row p (:234)
+        aff_normal = ((aff * m0).sum() / m0.sum()).reshape(1)
+        aff_abnormal = ((aff * m1).sum() / m1.sum()).reshape(1)
+        loss_constraint = (1 - (aff_normal - aff_abnormal)).clamp_min(min=0)     # (:236-240)
+        sq = torch.sum(torch.pow(combined - afn_all, 2), 1)
+        dist_ = torch.sqrt(torch.where(is_ab, sq, torch.ones_like(sq)))          # rows without label 1 never reach sqrt'(0)
+        loss_rec = (dist_ * m1).sum() / m1.sum()                                 # recon2 (:197-198)
+        return 1 * loss_cls + 1 * loss_constraint + 0.1 * loss_rec, loss_cls, loss_constraint, loss_rec
+
+    def loss_reference_path(self, nodes, labels):
         scores, to_feats_neigh, embeds, anomaly_feat, anomaly_feat_new = self.forward(nodes, labels, train_flag=True)
         target = labels.detach().to(scores.device, dtype=torch.float32)
         loss_cls = torch.mean(self.xent(scores.squeeze(), target))

@@ -532,7 +532,7 @@ def test_tiled_kernel_at_c4_slice():
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("path", [1, 2])
 @pytest.mark.parametrize("m,n,k", [(7535, 300, 748), (1300, 152, 300), (3000, 64, 20), (200, 64, 20), (129, 17, 65),
-                                   (1204, 76, 152)])
+                                   (1204, 76, 152), (39357, 300, 12)])
 def test_dense_matmul_layouts(path, m, n, k):
     """All three operand layouts the path uses (x W^T, dy W, dy^T x) on both code paths against fp64: rtol 1e-4 on
     the result scale (the tensor-core path splits fp32 into three bf16 terms: ~2^-22 relative per product)."""

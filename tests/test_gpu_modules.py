@@ -100,6 +100,15 @@ def test_minibatch_model_matches_reference(name):
     for k, g in c["grads"].items():
         p = dict(model.named_parameters())[k]
         assert_close(p.grad, g, rtol=GRAD_RTOL, atol=GRAD_ATOL, what=f"grad {k}")
+    # the composed path (forward -> affinity -> recon2 with boolean indexing, as the reference writes it) gives the
+    # same four numbers as the static-shape loss; so does a batch whose hop blocks came from the prefetch thread
+    for t, u in zip(model.loss_reference_path(nodes, labels), (total, cls, margin, rec)):
+        assert_close(t, u, rtol=1e-5, atol=1e-6, what="loss vs loss_reference_path")
+    pf = gs.BlockPrefetcher(agg, adj)
+    pf.submit(nodes)
+    for t, u in zip(model.loss(nodes, labels), (total, cls, margin, rec)):
+        assert torch.equal(t, u), "prefetched blocks changed the result"
+    agg.prefetcher = None
     with torch.no_grad():
         assert_close(model.to_prob(nodes, None), o["prob"], what="to_prob")
         to_feats, to_feats_neigh, mask = agg.forward(nodes, [adj[v] for v in nodes], adj, True)
