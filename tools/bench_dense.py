@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Time the dense projections of the GGAD path: ggad_dense_matmul (tcgen05 fp32-accurate GEMM / SIMT) next to
-torch's fp32 matmul (cuBLAS, TF32 off) on the shapes programs A and B run.
+"""Time the dense projections of the GGAD path: ggad_dense_matmul (tcgen05 fp32-accurate GEMM / SIMT, and what the
+auto dispatch picks) next to torch's fp32 matmul (cuBLAS, TF32 off) on the shapes programs A and B run -- forward
+(x W^T), data gradient (dy W) and weight gradient (dy^T x).
     python tools/bench_dense.py
 """
 import os
@@ -29,19 +30,25 @@ def timeit(fn, iters=20, warm=5):
     return float(np.median(ts))
 
 
-shapes = [("C1 layer 1: X W^T", 7535, 300, 748), ("C1 layer 2", 7535, 300, 300), ("C3 layer 2", 39357, 300, 300),
-          ("C3 layer 1 (d=10->12)", 39357, 300, 12), ("MLP fc1", 1300, 152, 300), ("mini-batch |U| x h x d", 3000, 64, 20),
+shapes = [("C1 layer 1", 7535, 300, 748), ("C1 layer 2", 7535, 300, 300), ("C2 layer 1 (d=25->28)", 11944, 300, 28),
+          ("C2 layer 2", 11944, 300, 300), ("C3 layer 1 (d=10->12)", 39357, 300, 12), ("C3 layer 2", 39357, 300, 300),
+          ("MLP fc1", 1300, 152, 300), ("MLP fc2", 1300, 76, 152), ("mini-batch |U| x h x d", 8000, 64, 20),
           ("C4 full-graph h=64", 3_700_550, 64, 20)]
-print(f"{'shape':32s} {'M':>8s} {'N':>5s} {'K':>5s} {'tcgen05 ms':>11s} {'TFLOP/s':>8s} {'SIMT ms':>9s} {'cuBLAS ms':>10s}  max rel err (tc / simt / cublas)")
+print(f"{'shape (M nodes, N out, K in)':30s} {'op':7s} {'auto ms':>8s} {'tcgen05':>8s} {'SIMT':>8s} {'cuBLAS':>8s}   rel err auto / cublas")
 for name, m, n, k in shapes:
-    x, w = torch.randn(m, k, device="cuda"), torch.randn(n, k, device="cuda")
-    ref = (x[:4096].double() @ w.double().t())
-    res = {}
-    for tag, fn in (("tc", lambda: ops.dense_matmul(x, w, trans_b=True, path=2)), ("simt", lambda: ops.dense_matmul(x, w, trans_b=True, path=1)),
-                    ("cublas", lambda: x @ w.t())):
-        t = timeit(fn)
-        err = ((fn()[:4096].double() - ref).abs().max() / ref.abs().max()).item()
-        res[tag] = (t, err)
-    fl = 2.0 * m * n * k
-    print(f"{name:32s} {m:8d} {n:5d} {k:5d} {res['tc'][0]:11.4f} {fl / res['tc'][0] / 1e9:8.2f} {res['simt'][0]:9.4f} {res['cublas'][0]:10.4f}"
-          f"  {res['tc'][1]:.2e} / {res['simt'][1]:.2e} / {res['cublas'][1]:.2e}")
+    x, w, dy = torch.randn(m, k, device="cuda"), torch.randn(n, k, device="cuda"), torch.randn(m, n, device="cuda")
+    ops_ = [("x W^T", lambda p: ops.dense_matmul(x, w, trans_b=True, path=p), lambda: x @ w.t(), lambda: x[:4096].double() @ w.double().t(), slice(0, 4096)),
+            ("dy W", lambda p: ops.dense_matmul(dy, w, path=p), lambda: dy @ w, lambda: dy[:4096].double() @ w.double(), slice(0, 4096)),
+            ("dy^T x", lambda p: ops.dense_matmul(dy, x, trans_a=True, path=p), lambda: dy.t() @ x, lambda: dy.double().t() @ x.double(), slice(None))]
+    for tag, ours, cublas, ref_fn, sl in ops_:
+        ref = ref_fn()
+        t = {}
+        for key, p in (("auto", 0), ("tc", 2), ("simt", 1)):
+            try:
+                t[key] = timeit(lambda: ours(p))
+            except RuntimeError:
+                t[key] = float("nan")
+        t["cublas"] = timeit(cublas)
+        e_auto = ((ours(0)[sl].double() - ref).abs().max() / ref.abs().max()).item()
+        e_cub = ((cublas()[sl].double() - ref).abs().max() / ref.abs().max()).item()
+        print(f"{name:30s} {tag:7s} {t['auto']:8.4f} {t['tc']:8.4f} {t['simt']:8.4f} {t['cublas']:8.4f}   {e_auto:.1e} / {e_cub:.1e}")
