@@ -424,8 +424,13 @@ class GCN(nn.Module):
                 return self.loss_reference_path(nodes, labels)
         neigh_feats, neigh_feats_expand, mask = enc.aggregator.forward(nodes, _LazyNeighs(enc.adj_lists, nodes),
                                                                        enc.adj_lists, True)
-        dev = neigh_feats.device
-        lab = lab.to(dev).reshape(-1)
+        return self.loss_from_aggregates(neigh_feats, neigh_feats_expand, mask, lab.to(neigh_feats.device).reshape(-1))
+
+    def loss_from_aggregates(self, neigh_feats, neigh_feats_expand, mask, lab):
+        """The dense tail of a training batch from the two aggregates ([B,d] and [|U|,d], rows beyond |U| may be zero
+        padding), the ego-mean mask (anything with ``.mm``) and the device label vector: every shape is static, which
+        is what train.GraphedMiniBatchStep captures into a CUDA graph."""
+        enc = self.enc
         is_ab = lab == 1
         m1 = is_ab.to(torch.float32)
         m0 = (lab == 0).to(torch.float32)

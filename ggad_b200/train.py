@@ -81,6 +81,147 @@ class GraphedFullBatchStep:
         return self._eager()
 
 
+class GraphedMiniBatchStep:
+    """Program B's training batch (src/model_handler.py:330-364) with the dense tail, the backward pass and Adam in
+    ONE CUDA-graph launch.
+
+    What varies from batch to batch is integer work -- the frontier U, the hop blocks, their sizes -- and it stays
+    eager (device kernels, prefetchable with graphsage.BlockPrefetcher).  Everything after the two table gathers has
+    static shapes once the |U|-sized tensors are padded to a capacity: the gathers write straight into static buffers
+    (rows beyond |U| are zero and are referenced by no block column, so they contribute exact zeros to every sum and
+    gradient), the hop-1 ego-mean operator and its transpose are copied into fixed-size CSR buffers, and one replay
+    runs ~150 small kernels (projections, ego mean, outlier generation, the three losses, their backward, Adam) that
+    cost 3.3 ms of host time when issued eagerly.  Capacities grow by doubling (one re-capture).  Results equal
+    ``model.loss(...).backward(); opt.step()`` (tested)."""
+
+    def __init__(self, model, lr: float = 1e-3, weight_decay: float = 0.0, batch_rows: int = 200, u_cap: int = 1 << 14,
+                 e_cap: int = 1 << 16, warmup: int = 2, group=None):
+        import torch.distributed as dist
+        from . import graphsage as gs
+        self.model, self.gs = model, gs
+        self.enc, self.agg = model.enc, model.enc.aggregator
+        self.dev = gs._device_of(self.enc.features)
+        self.lr, self.wd, self.b, self.warmup = lr, weight_decay, int(batch_rows), warmup
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.dist, self.group = dist, group
+        # with one rank Adam is part of the graph; data parallel: fwd + bwd are graphed, the gradient all-reduce and a
+        # fused Adam step follow eagerly
+        self.opt = torch.optim.Adam(self.params, lr=lr, weight_decay=weight_decay, capturable=True, fused=self.world > 1 or None)
+        self.graph = None
+        self._alloc(u_cap, e_cap)
+
+    def _alloc(self, u_cap, e_cap):
+        dev, b = self.dev, self.b
+        table = self.gs._feature_table(self.enc.features)
+        dp = table.shape[1]
+        self.u_cap, self.e_cap = int(u_cap), int(e_cap)
+        self.to_feats = torch.zeros(b, dp, device=dev)
+        self.to_feats_neigh = torch.zeros(self.u_cap, dp, device=dev)
+        self.lab = torch.zeros(b, dtype=torch.int64, device=dev)
+        z64 = lambda n: torch.zeros(n, dtype=torch.int64, device=dev)
+        z32 = lambda n: torch.zeros(n, dtype=torch.int32, device=dev)
+        # ego-mean operator M = mask / rdeg over the hop-1 block [B, |U|] and its transpose [u_cap, B] (per-edge values)
+        self.m_rowptr, self.m_col, self.m_rs = z64(b + 1), z32(self.e_cap), torch.zeros(b, device=dev)
+        self.t_rowptr, self.t_col, self.t_val = z64(self.u_cap + 1), z32(self.e_cap), torch.zeros(self.e_cap, device=dev)
+        g = CSRGraph(self.m_rowptr, self.m_col, None, b, self.u_cap, row_scale=self.m_rs, use_plan=False)
+        gt = CSRGraph(self.t_rowptr, self.t_col, self.t_val, self.u_cap, b, use_plan=False)
+        g._T, gt._T = gt, g
+        outer = self
+
+        class _Mask:                       # what loss_from_aggregates calls .mm on
+            def mm(self, x):
+                from . import ops
+                return ops.spmm(g, x.contiguous())
+        self.mask = _Mask()
+        self.graph, self.out = None, None
+
+    def _tail(self):
+        for p in self.params:
+            p.grad = None
+        out = self.model.loss_from_aggregates(self.to_feats[:, :self.enc.feat_dim], self.to_feats_neigh[:, :self.enc.feat_dim],
+                                              self.mask, self.lab)
+        out[0].backward()
+        if self.world == 1:
+            self.opt.step()
+        return tuple(t.detach() for t in out)
+
+    def _capture(self):
+        dev = self.dev
+        state = [p.detach().clone() for p in self.params]
+        # a re-capture (capacity growth in the middle of training) must not disturb the optimiser: snapshot its state
+        keys = ("step", "exp_avg", "exp_avg_sq")
+        snap = {id(p): {k: self.opt.state[p][k].clone() for k in keys} for p in self.params if self.opt.state.get(p)}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, self.warmup)):          # warms the allocator, creates the Adam state tensors
+                self._tail()
+                if self.world > 1:
+                    self.opt.step()
+            with torch.no_grad():
+                for p, s_ in zip(self.params, state):
+                    p.copy_(s_)
+            for p in self.params:
+                st = self.opt.state[p]
+                for k in keys:
+                    if id(p) in snap:
+                        st[k].copy_(snap[id(p)][k])
+                    else:
+                        st[k].zero_()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self._tail()
+
+    def _load(self, nodes, labels):
+        """Eager, per batch: hop blocks (or the prefetched ones), the two gathers from the feature table into the static
+        buffers, the ego-mean operator and its transpose into the fixed-size CSR buffers."""
+        from . import ops
+        gs, dev = self.gs, self.dev
+        ready = self.agg.prefetcher.take(nodes) if getattr(self.agg, "prefetcher", None) is not None else None
+        hop1 = ready[0] if ready else gs._block_for(nodes, None, self.enc.adj_lists, True, dev)
+        hop2 = ready[1] if ready else gs._block_for(hop1.frontier_d, None, self.enc.adj_lists, False, dev)
+        self.agg.last_blocks = (hop1, hop2)
+        assert hop1.n_rows == self.b, f"GraphedMiniBatchStep was built for {self.b}-node batches, got {hop1.n_rows}"
+        e1 = int(hop1.col_d.numel())
+        if hop1.n_cols > self.u_cap or e1 > self.e_cap:                     # grow once, re-capture
+            self._alloc(max(self.u_cap, 2 * hop1.n_cols), max(self.e_cap, 2 * e1))
+        table = gs._feature_table(self.enc.features)
+        u = hop1.n_cols
+        ops.gather_reduce(hop1.graph("sym"), table, xmap=hop1.frontier_d, y_out=self.to_feats)
+        self.to_feats_neigh[u:].zero_()
+        ops.gather_reduce(hop2.graph("sym"), table, xmap=hop2.frontier_d, y_out=self.to_feats_neigh[:u])
+        gm = hop1.graph("mean")
+        gt = gm.T                                                            # device transpose; 1/rdeg folded into values
+        self.m_rowptr.copy_(gm.rowptr)
+        self.m_col[:e1].copy_(gm.col)
+        self.m_rs.copy_(gm.row_scale)
+        self.t_rowptr[:u + 1].copy_(gt.rowptr)
+        self.t_rowptr[u + 1:].fill_(e1)                                      # padding rows are empty
+        self.t_col[:e1].copy_(gt.col)
+        self.t_val[:e1].copy_(gt.val)
+        self.lab.copy_(labels.reshape(-1), non_blocking=True)
+
+    def step(self, nodes, labels):
+        """One batch; returns (total, cls, margin, rec) as static device tensors."""
+        self._load(nodes, labels)
+        if self.graph is None:
+            self._capture()
+        self.graph.replay()
+        if self.world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in self.params])
+            self.dist.all_reduce(flat, group=self.group)
+            flat /= self.world
+            o = 0
+            for p in self.params:
+                p.grad.copy_(flat[o:o + p.numel()].reshape(p.shape))
+                o += p.numel()
+            self.opt.step()
+        return self.out
+
+
 class DataParallelMiniBatch:
     """Data-parallel driver of program B's training batch (src/model_handler.py:330-364) for N GPUs.
 

@@ -382,3 +382,52 @@ def test_sharded_sage_single_rank_matches_oracle():
     assert_close(loss, ref, what="loss")
     for a, b, k in zip(wd, wc, ("w1", "w2", "w_cls")):
         assert_close(a.grad, b.grad, rtol=GRAD_RTOL, atol=GRAD_ATOL, what=f"grad {k}")
+
+
+def test_graphed_minibatch_step_matches_eager():
+    """f2 for program B: dense tail + backward + Adam as one CUDA-graph replay per batch (train.GraphedMiniBatchStep,
+    static buffers padded to a capacity, incl. one capacity growth + re-capture and prefetched hop blocks) follows the
+    same parameter trajectory as loss() / backward() / Adam issued eagerly."""
+    import copy
+    from ggad_b200 import graphsage as gs, synth
+    from ggad_b200.train import GraphedMiniBatchStep
+    n, d, h, B = 30000, 17, 32, 48
+    adj = synth.rmat_adjacency(n, 200000, seed=4, device="cuda")
+    rng = np.random.default_rng(4)
+    feats = torch.nn.Embedding(n, d)
+    feats.weight = torch.nn.Parameter(torch.from_numpy(rng.random((n, d), dtype=np.float32)), requires_grad=False)
+    feats = feats.cuda()
+    cand = np.flatnonzero((adj.rowptr[1:] - adj.rowptr[:-1]).cpu().numpy() > 0)
+    batches = [rng.choice(cand, B, replace=False).tolist() for _ in range(5)]
+    labels = [torch.from_numpy((rng.random(B) < 0.25).astype(np.int64)) for _ in range(5)]
+
+    def make():
+        torch.manual_seed(3)
+        agg = gs.GCNAggregator(feats, cuda=True)
+        enc = gs.GCNEncoder(feats, d, h, adj, agg, gcn=True, cuda=True)
+        return gs.GCN(2, enc).cuda(), agg
+    ref, _ = make()
+    opt = torch.optim.Adam([p for p in ref.parameters() if p.requires_grad], lr=1e-2, weight_decay=0.007)
+    ref_losses = []
+    for nodes, lab in zip(batches, labels):
+        opt.zero_grad()
+        out = ref.loss(nodes, lab)
+        out[0].backward()
+        opt.step()
+        ref_losses.append([float(t) for t in out])
+    m, agg = make()
+    step = GraphedMiniBatchStep(m, lr=1e-2, weight_decay=0.007, batch_rows=B, u_cap=64, e_cap=128)   # forces a growth
+    pf = gs.BlockPrefetcher(agg, adj)
+    pf.submit(batches[0])
+    for i, (nodes, lab) in enumerate(zip(batches, labels)):
+        if i + 1 < len(batches):
+            pf.submit(batches[i + 1])
+        if i == 3:                                   # capacity growth in the middle of training -> re-capture
+            step._alloc(2 * step.u_cap, 2 * step.e_cap)
+        out = step.step(nodes, lab)
+        got = [float(t) for t in out]
+        assert np.allclose(got, ref_losses[i], rtol=2e-4, atol=1e-6), (i, got, ref_losses[i])
+    assert step.u_cap > 64 and step.graph is not None
+    for (k, a), (_, b) in zip(m.named_parameters(), ref.named_parameters()):
+        if a.requires_grad:
+            assert_close(a, b, rtol=2e-4, atol=2e-6, what=f"parameter {k} after 5 graphed batches")

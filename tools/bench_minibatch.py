@@ -40,6 +40,8 @@ def main():
                     help="hint for DeviceAdjacency.reserve_edges: grow the memory pools ONCE for hop blocks of up to this "
                          "many edges (a new maximum later costs a cudaMalloc, ~1.5 s when the memory is peer-mapped on an "
                          "8-GPU box).  -1 = twice the largest block of the warm-up batches, 0 = no hint")
+    ap.add_argument("--graphed", action="store_true",
+                    help="train.GraphedMiniBatchStep: dense tail + backward + Adam replayed as one CUDA graph per batch")
     ap.add_argument("--no-prefetch", action="store_true", help="build every batch's hop blocks inside the step (no input pipeline)")
     ap.add_argument("--diag", action="store_true", help="also time the rank-local part of every batch (adds a sync)")
     ap.add_argument("--phases", action="store_true",
@@ -70,6 +72,10 @@ def main():
     model = gs.GCN(2, enc).to(dev)
     opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3, weight_decay=0.007)
     dp = DataParallelMiniBatch(model, opt)
+    graphed = None
+    if args.graphed:
+        from ggad_b200.train import GraphedMiniBatchStep
+        graphed = GraphedMiniBatchStep(model, lr=1e-3, weight_decay=0.007, batch_rows=args.batch + args.seeds)
     rng = np.random.default_rng(72 + 1000 * rank)                 # ... and different seed batches
     deg = (adj.rowptr[1:] - adj.rowptr[:-1]).cpu().numpy()
     cand = np.flatnonzero(deg > 0)
@@ -86,6 +92,8 @@ def main():
         upcoming.append(rng.choice(cand, B, replace=False).tolist())
         if prefetch:
             prefetch.submit(upcoming[0])         # batch i+1's frontier is built while batch i trains
+        if graphed is not None:
+            return graphed.step(nodes, labels)[0]
         if args.diag:
             opt.zero_grad(set_to_none=True)
             t0 = time.perf_counter()
@@ -162,7 +170,7 @@ def main():
            "wall_ms_per_lockstep_batch": float(wall.item()) / args.iters * 1e3, "max_ms_per_batch_rank0": float(st[:, 0].max()), "ggad_launches_per_batch": float(np.mean(st[:, 1])),
            "mean_frontier_U": float(np.mean(st[:, 2])), "mean_hop1_edges": float(np.mean(st[:, 3])),
            "mean_frontier_U2": float(np.mean(st[:, 4])), "mean_hop2_edges": float(np.mean(st[:, 5])),
-           "edges_per_s": edges * agg_bps, "loss": lv, "prefetch_next_batch_blocks": prefetch is not None,
+           "edges_per_s": edges * agg_bps, "loss": lv, "prefetch_next_batch_blocks": prefetch is not None, "cuda_graph_tail": graphed is not None,
            "reference_cpu_s_per_batch_300k_proxy_survey": 1.52}
     if args.phases:
         out["phase_ms_mean"] = {k: round(float(np.mean(v[-3 * args.iters // 4:])) * (len(v) / (args.iters + args.warm)), 3) for k, v in phase_ms.items()}
