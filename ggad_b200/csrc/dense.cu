@@ -117,8 +117,11 @@ int dense_matmul_impl(int trans_a, int trans_b, int64_t M, int64_t N, int64_t K,
   // few output tiles and a long k loop (dW = dY^T X: K = number of nodes) would leave most SMs idle: those go to the
   // split-K SIMT path below
   const int64_t tc_tiles = ((M + 127) / 128) * ((N + 127) / 128);
-  const bool skinny = tc_tiles < 48 && K >= 4096 && !(trans_a && !getenv("GGAD_DENSE_NO_STREAMK"));   // A^T B runs stream-K
-  const bool big = M >= 64 && N >= 16 && K >= 8 && M * N * K >= (1ll << 18) && !skinny;
+  // (measured, profiles/r02h_dense_projections.txt: the stream-K A^T B kernel wins from 300 x 300 outputs up --
+  // C3 layer 2: 0.22 ms vs 0.65 ms SIMT / 0.29 ms cuBLAS -- and loses below, e.g. 64 x 20 x 8000: 0.20 vs 0.07 ms)
+  const bool streamk_ok = trans_a && M >= 128 && N >= 128 && !getenv("GGAD_DENSE_NO_STREAMK");
+  const bool skinny = tc_tiles < 48 && K >= 4096 && !streamk_ok;
+  const bool big = M >= 64 && N >= 8 && K >= 8 && M * N * K >= (1ll << 18) && !skinny && (!trans_a || streamk_ok || tc_tiles >= 48);
   GGAD_REQUIRE(path != 2 || (aligned && layout_ok && K > 0), GGAD_ERR_UNSUPPORTED,
                "dense_matmul: the tensor-core path needs 16-byte aligned operands and not both operands transposed");
   if (K > 0 && aligned && layout_ok && (path == 2 || (path == 0 && big))) {
@@ -147,9 +150,9 @@ int dense_matmul_impl(int trans_a, int trans_b, int64_t M, int64_t N, int64_t K,
   const int64_t tiles = int64_t(grid.x) * grid.y;
   const int sms = sm_count_cached();
   int splits = 1;
-  if (sms > 0 && tiles < 2 * sms && K >= 2048) {
+  if (sms > 0 && tiles < 2 * sms && K >= 512) {
     splits = int((3ll * sms + tiles - 1) / tiles);                 // ~3 CTAs per SM in total
-    if (splits > K / 256) splits = int(K / 256);
+    if (splits > K / 128) splits = int(K / 128);
     if (splits > 256) splits = 256;
   }
   if (splits > 1) {

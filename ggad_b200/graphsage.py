@@ -289,8 +289,11 @@ class BlockPrefetcher:
         for i: pf.submit(batch_{i+1});  model.loss(batch_i, labels_i) ...     # forward picks the prepared blocks up
     """
 
-    def __init__(self, aggregator: "GCNAggregator", adj_lists):
+    def __init__(self, aggregator: "GCNAggregator", adj_lists, switch_interval: float = 2e-4):
+        import sys
         import threading
+        if switch_interval and sys.getswitchinterval() > switch_interval:
+            sys.setswitchinterval(switch_interval)     # the helper needs the GIL for microseconds at a time; 5 ms slices starve it
         self.agg, self.adj_lists = aggregator, adj_lists
         self.device = _device_of(aggregator.features)
         self.stream = torch.cuda.Stream(device=self.device)

@@ -130,9 +130,16 @@ def _worker(rank, world, port, q):
         dx64 = a64.T @ y64
         for got, ref, mag, what in ((y, y64, abs(a64) @ np.abs(x.double().cpu().numpy()), "y"),
                                     (dx, dx64, abs(a64.T) @ np.abs(y64), "dx")):
-            worst = float((np.abs(got.double().cpu().numpy() - ref) / (1e-4 * np.abs(ref) + 1e-5 * mag + 1e-30)).max())
+            ratio = np.abs(got.double().cpu().numpy() - ref) / (1e-4 * np.abs(ref) + 1e-5 * mag + 1e-30)
+            worst = float(ratio.max())
             ok = ok and worst <= 1.0
             oracle_worst[what] = round(worst, 4)
+            if worst > 1.0:                       # diagnostics: where, how big, how many
+                r_, c_ = np.unravel_index(int(ratio.argmax()), ratio.shape)
+                oracle_worst[what + "_at"] = dict(row=int(r_), col=int(c_), got=float(got[r_, c_]), ref=float(ref[r_, c_]),
+                                                  mag=float(mag[r_, c_]), n_bad=int((ratio > 1).sum()),
+                                                  rows_bad=int((ratio > 1).any(1).sum()),
+                                                  out_deg=int((full.col == int(r_)).sum()), in_deg=int(full.rowptr[r_ + 1] - full.rowptr[r_]))
         # exact integer check: the transposed shards tile the global transpose
         assert int(bwd.nnz) > 0
     tot = torch.tensor([bwd.nnz], device=dev)

@@ -32,7 +32,10 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--warm", type=int, default=3)
     ap.add_argument("--mode", default="both", choices=["sharded", "replicated", "both"])
-    ap.add_argument("--even-ranges", action="store_true", help="sharded mode: equal node ranges instead of entry-balanced ones")
+    ap.add_argument("--balanced", action="store_true",
+                    help="sharded mode: column ranges balanced by adjacency entries (+ 4 per table row) instead of equal node "
+                         "ranges.  Measured SLOWER at N=2 (19.2 vs 9.5 ms/step, profiles/r02h_sharded_sage_n2_balanced.json): "
+                         "the hot rank's frontier blocks grow with its share of the hub columns; kept as an option")
     args = ap.parse_args()
     import torch.distributed as dist
     from ggad_b200 import _lib, sharded, synth
@@ -49,7 +52,7 @@ def main():
     # count -- on a power-law graph the first node range holds most of the edges (R-MAT: 44 % of the sources of the
     # 8-shard graph fall into shard 0), and the slowest rank sets the step time.  Exact integer histogram, all-reduced.
     lo, hi = rank * n_local, (rank + 1) * n_local
-    if world > 1 and not args.even_ranges:
+    if world > 1 and args.balanced:
         from ggad_b200 import dist as gdist
         mine = synth.rmat_shard(n_local, m_local, world, rank, seed=0, device=dev, mean=False)
         cnt = torch.empty(n_glob, dtype=torch.int32, device=dev)
