@@ -52,6 +52,7 @@ def main():
     ap.add_argument("--epochs", type=int, default=20)
     ap.add_argument("--cpu-epochs", type=int, default=1)
     ap.add_argument("--h", type=int, default=300)
+    ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay part (for kernel launch lists)")
     args = ap.parse_args()
     import oracle
     from ggad_b200 import _lib, graph, losses, model
@@ -101,9 +102,9 @@ def main():
     from ggad_b200 import train
     m_g = model.Model(d, h, "prelu", 1, "avg")
     m_g.load_state_dict(state)
-    stepper = train.GraphedFullBatchStep(m_g.cuda(), xt, g_hat, g_r, normal, abnormal, ns)
-    tg = []
-    for _ in range(args.epochs + 3):
+    stepper = None if args.no_graph else train.GraphedFullBatchStep(m_g.cuda(), xt, g_hat, g_r, normal, abnormal, ns)
+    tg = [(float("nan"), float("nan"))] * 4 if args.no_graph else []
+    for _ in range(0 if args.no_graph else args.epochs + 3):
         noise = torch.randn(1, len(abnormal), h, generator=gen) * var + mean
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
