@@ -119,7 +119,8 @@ int dense_matmul_impl(int trans_a, int trans_b, int64_t M, int64_t N, int64_t K,
   const int64_t tc_tiles = ((M + 127) / 128) * ((N + 127) / 128);
   // (measured, profiles/r02h_dense_projections.txt: the stream-K A^T B kernel wins from 300 x 300 outputs up --
   // C3 layer 2: 0.22 ms vs 0.65 ms SIMT / 0.29 ms cuBLAS -- and loses below, e.g. 64 x 20 x 8000: 0.20 vs 0.07 ms)
-  const bool streamk_ok = trans_a && M >= 128 && N >= 128 && !getenv("GGAD_DENSE_NO_STREAMK");
+  // (... and again for very long k loops: 64 x 20 x 3.7 M runs 1.73 ms stream-K vs 4.16 ms SIMT split-K)
+  const bool streamk_ok = trans_a && ((M >= 128 && N >= 128) || K >= (1ll << 18)) && !getenv("GGAD_DENSE_NO_STREAMK");
   const bool skinny = tc_tiles < 48 && K >= 4096 && !streamk_ok;
   const bool big = M >= 64 && N >= 8 && K >= 8 && M * N * K >= (1ll << 18) && !skinny && (!trans_a || streamk_ok || tc_tiles >= 48);
   GGAD_REQUIRE(path != 2 || (aligned && layout_ok && K > 0), GGAD_ERR_UNSUPPORTED,

@@ -328,6 +328,13 @@ __device__ __forceinline__ void push_rows(const GatherArgs& a, int64_t ra, int64
 #ifndef GGAD_LIGHT_ROLLED
 #define GGAD_LIGHT_ROLLED 0
 #endif
+// Hybrid staging (A/B knob, round 2): besides the U neighbor rows a lane group keeps in flight in REGISTERS, GGAD_SMEM_ROWS
+// more rows per batch are fetched with cp.async (LDGSTS, no destination registers) into a per-thread slot of shared
+// memory and consumed after the register part -- more bytes in flight per SM than the 64-register budget allows
+// (the kernel is latency-bound at 46 % occupancy, profiles/r02a_ncu_*).  Same summation order, bit-identical results.
+#ifndef GGAD_SMEM_ROWS
+#define GGAD_SMEM_ROWS 0
+#endif
 template <int G, int CH>
 __device__ __forceinline__ void push_group_rows(const GatherArgs& a, int64_t ra, int64_t rb, int gl) {
   if (a.y == nullptr) return;
@@ -404,7 +411,8 @@ struct TileSmem {
   static constexpr int kFlag = kCj + ((NGRP + 1 + 3) / 4) * 16;    // int32[NGRP] (+pad)
   static constexpr int kPart = kFlag + ((NGRP + 3) / 4) * 16;      // float4[NGRP][2][G*CH]
   static constexpr int kBias = kPart + NGRP * 2 * G * CH * 16;     // float4[G*CH] bias row (light epilogue only)
-  static constexpr int kBytes = kBias + (BIAS ? G * CH * 16 : 0);
+  static constexpr int kRows = kBias + (BIAS ? G * CH * 16 : 0);   // float4[GGAD_SMEM_ROWS][kThreads] cp.async slots
+  static constexpr int kBytes = kRows + ((CH == 1) ? GGAD_SMEM_ROWS * kThreads * 16 : 0);
 };
 
 // MODE 0: unweighted (val == NULL), 1: per-edge val, 2: general (col_scale / xmap, optional val).
@@ -601,6 +609,55 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
       }
     } else {
       int e = j1;
+#if GGAD_SMEM_ROWS > 0
+      if constexpr (CH == 1 && MODE < 2) {
+        constexpr int US = GGAD_SMEM_ROWS, UB = U + US;
+        float4* my_rows = reinterpret_cast<float4*>(smem + L::kRows) + tid;     // slot s at my_rows[s * kThreads]
+        const uint32_t my_rows_s = smem_u32(my_rows);
+        for (; e + UB <= j2; e += UB) {
+          int c[U];
+          float w[U], ws_[US];
+          float4 xv[U][CH];
+          // shared-memory part first, so that all UB rows are in flight together
+#pragma unroll
+          for (int q = 0; q < US; ++q) {
+            const int cq = sc[e + U + q];
+            ws_[q] = (MODE == 0) ? 1.f : sv[e + U + q];
+            const char* src = lane_base[0] + uint64_t(uint32_t(cq)) * row_bytes;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(my_rows_s + uint32_t(q) * (kThreads * 16u)), "l"(src) : "memory");
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            c[u] = sc[e + u];
+            w[u] = (MODE == 0) ? 1.f : sv[e + u];
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) xv[u][0] = load_chunk(c[u], 0);
+          const bool inside = e + UB <= cur_end;
+          if (inside) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) accumulate(w[u], xv[u]);
+          } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              while (e + u >= cur_end) flush();
+              accumulate(w[u], xv[u]);
+            }
+          }
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+          for (int q = 0; q < US; ++q) {
+            float4 xs[CH];
+            xs[0] = my_rows[q * kThreads];
+            if (!inside) {
+              while (e + U + q >= cur_end) flush();
+            }
+            accumulate(ws_[q], xs);
+          }
+        }
+      }
+#endif
       // full batches of U edges: U independent 128-bit gathers per lane in flight
       for (; e + U <= j2; e += U) {
         int c[U];
