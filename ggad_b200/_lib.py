@@ -82,6 +82,7 @@ SIGNATURES = {
     "ggad_block_fill": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp]),
     "ggad_unique_sorted": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
     "ggad_block_remap": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp]),
+    "ggad_block_col_weights": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "ggad_rmat_keys": (C.c_int, [_vp, _i64, _i64, _i32, _i32, C.c_uint64, _f, _f, _f, _i64, _i64, _vp, _vp]),
     "ggad_spmm_fwd_bwd_host": (C.c_int, [C.POINTER(ResidentCSR), C.POINTER(ResidentCSR), _vp, _vp, _vp, _vp, _i32,
                                          _vp, _vp, _vp, _vp, _vp]),

@@ -372,6 +372,26 @@ int col_histogram_impl(const int32_t* col, int64_t nnz, int32_t* counts, int64_t
 }
 
 
+// val[e] = 1 / sqrt(counts[col[e]]): the batch-local column normalisation of a hop block as a per-edge value
+__global__ void edge_inv_sqrt_count_kernel(const int32_t* __restrict__ col, int64_t nnz, const int32_t* __restrict__ counts,
+                                           float* __restrict__ val) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < nnz; e += stride)
+    val[e] = __fdiv_rn(1.f, __fsqrt_rn(float(__ldg(counts + col[e]))));
+}
+
+int block_col_weights_impl(const int32_t* col, int64_t nnz, int32_t* counts, int64_t n_nodes, float* val, cudaStream_t st) {
+  GGAD_REQUIRE(counts && val && n_nodes >= 0 && nnz >= 0 && (nnz == 0 || col), GGAD_ERR_INVALID, "block_col_weights: bad arguments");
+  int rc = col_histogram_impl(col, nnz, counts, n_nodes, st);
+  if (rc != GGAD_OK || nnz == 0) return rc;
+  unsigned blocks = blocks_for(nnz);
+  if (blocks > 148u * 32u) blocks = 148u * 32u;
+  edge_inv_sqrt_count_kernel<<<blocks, 256, 0, st>>>(col, nnz, counts, val);
+  GGAD_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return GGAD_OK;
+}
+
 int block_rowptr_impl(const int64_t* rowptr, const int32_t* col, int64_t n_nodes, const int32_t* nodes, int64_t n_batch,
                       int add_self, int64_t* block_rowptr, int64_t* nnz_host, cudaStream_t st) {
   GGAD_REQUIRE(rowptr && (nodes || n_batch == 0) && block_rowptr && nnz_host && n_batch >= 0 && n_nodes >= 0,

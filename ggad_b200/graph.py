@@ -363,6 +363,40 @@ class DeviceAdjacency:
         return dict(frontier=uniq[:k], rowptr=block_rowptr, col=local[:m], cdeg=cdeg[:k], n_rows=nb, n_cols=k)
 
 
+def _block_direct(self, nodes: torch.Tensor, add_self: bool):
+    """Hop block for a gather straight from the feature table: rows = ``nodes``, columns = GLOBAL neighbor ids, per-edge
+    value 1/sqrt(batch-local column degree) from an exact integer histogram (ggad_block_col_weights).  No frontier list,
+    no local ids: no sort / unique / remap and one size read-back instead of two."""
+    import ctypes as C
+    dev = self.device
+    nodes = nodes.to(device=dev, dtype=torch.int32).contiguous()
+    nb = int(nodes.numel())
+    block_rowptr = torch.empty(nb + 1, dtype=torch.int64, device=dev)
+    nnz = C.c_int64(0)
+    h = lib()
+    with torch.cuda.device(dev):
+        st = stream_ptr(dev)
+        check(h.ggad_block_rowptr(ptr(self.rowptr), ptr(self.col), self.n, ptr(nodes), nb, int(add_self),
+                                  ptr(block_rowptr), C.addressof(nnz), st))
+        m = int(nnz.value)
+        self._reserve(max(m, int(self.reserve_edges)), st)          # allocator priming at new maxima (see _reserve)
+        cols = torch.empty(max(m, 1), dtype=torch.int32, device=dev)
+        check(h.ggad_block_fill(ptr(self.rowptr), ptr(self.col), self.n, ptr(nodes), nb, int(add_self),
+                                ptr(block_rowptr), ptr(cols), st))
+        # one histogram scratch per stream (the prefetch thread builds blocks on its own stream)
+        key = torch.cuda.current_stream(dev).cuda_stream
+        counts = self.__dict__.setdefault("_counts", {}).get(key)
+        if counts is None:
+            counts = torch.empty(self.n, dtype=torch.int32, device=dev)
+            self._counts[key] = counts
+        val = torch.empty(max(m, 1), dtype=torch.float32, device=dev)
+        check(h.ggad_block_col_weights(ptr(cols), m, ptr(counts), self.n, ptr(val), st))
+    return dict(rowptr=block_rowptr, col=cols[:m], val=val[:m], n_rows=nb, n_cols=self.n)
+
+
+DeviceAdjacency.block_direct = _block_direct
+
+
 def batch_block(adj: AdjListCSR, nodes: Sequence[int], add_self: bool):
     """Frontier + local block CSR for one aggregation hop (the set unions of
     src/graphsage.py:305-311,335-341 as array ops).  Returns dict with:

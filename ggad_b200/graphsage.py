@@ -147,9 +147,57 @@ def _block_for(nodes, to_neighs, adj_lists, add_self, device) -> _Block:
     return _Block.from_host(rowptr, cols, device)
 
 
-def _aggregate(block: _Block, mode: str, features, device) -> torch.Tensor:
-    """(weights of ``mode``) @ features[frontier]  -> [rows, d]."""
+class _DirectBlock:
+    """A hop block that is only gathered from the feature table (hop 2 of GCNAggregator): global column ids and the
+    batch-local 1/sqrt(cdeg) as per-edge values (DeviceAdjacency.block_direct) -- sym-norm aggregation without the
+    frontier list.  ``n_cols`` / ``frontier`` are derived on demand (statistics and tests only)."""
+
+    def __init__(self, b, device):
+        self.n_rows, self.device = int(b["n_rows"]), device
+        self.rowptr_d, self.col_d, self.val_d, self.n_table = b["rowptr"], b["col"], b["val"], int(b["n_cols"])
+        self.rdeg_i = self.rowptr_d[1:] - self.rowptr_d[:-1]
+        self.rdeg_d = self.rdeg_i.to(torch.float32)
+
+    @property
+    def frontier_d(self):
+        return torch.unique(self.col_d)
+
+    @property
+    def frontier(self):
+        return self.frontier_d.cpu().numpy().astype(np.int64)
+
+    @property
+    def n_cols(self):
+        return int(self.frontier_d.numel())
+
+    def graph(self, mode: str) -> CSRGraph:
+        assert mode == "sym"
+        return CSRGraph(self.rowptr_d, self.col_d, self.val_d, self.n_rows, self.n_table, row_scale=1.0 / self.rdeg_d.sqrt())
+
+    def tensors(self):
+        return (self.rowptr_d, self.col_d, self.val_d, self.rdeg_i, self.rdeg_d)
+
+
+def _hop2_block(frontier_d: torch.Tensor, adj_lists, features, device):
+    """Hop-2 block of a training batch: the direct form when the features are a table on this device."""
+    adj_dev = adj_lists if hasattr(adj_lists, "block") else AdjListCSR.get(adj_lists).device(device)
+    if isinstance(features, nn.Embedding) and hasattr(adj_dev, "block_direct"):
+        return _DirectBlock(adj_dev.block_direct(frontier_d, False), device)
+    return _block_for(frontier_d, None, adj_lists, False, device)
+
+
+def _aggregate(block, mode: str, features, device, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(weights of ``mode``) @ features[frontier]  -> [rows, d] (``out``: padded-width destination, returned as is)."""
     g = block.graph(mode)
+    if isinstance(block, _DirectBlock):
+        table = _feature_table(features)
+        if out is not None:
+            ops.gather_reduce(g, table, y_out=out)
+            return out
+        return ops.spmm(g, table)[:, :features.weight.shape[1]]
+    if out is not None:
+        ops.gather_reduce(g, _feature_table(features), xmap=block.frontier_d, y_out=out)
+        return out
     table = _feature_table(features)
     if table is not None:
         d = features.weight.shape[1]
@@ -270,7 +318,7 @@ class GCNAggregator(nn.Module):
         to_feats = _aggregate(hop1, "sym", self.features, device)
         to_feats_neigh = None
         if train_flag == True:
-            hop2 = ready[1] if ready else _block_for(hop1.frontier_d, None, adj_list, False, device)   # no self union (:335)
+            hop2 = ready[1] if ready else _hop2_block(hop1.frontier_d, adj_list, self.features, device)   # no self union (:335)
             to_feats_neigh = _aggregate(hop2, "sym", self.features, device)
             self.last_blocks = (hop1, hop2)
         else:
@@ -305,7 +353,7 @@ class BlockPrefetcher:
         try:
             with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
                 hop1 = _block_for(nodes, None, self.adj_lists, True, self.device)
-                hop2 = _block_for(hop1.frontier_d, None, self.adj_lists, False, self.device)
+                hop2 = _hop2_block(hop1.frontier_d, self.adj_lists, self.agg.features, self.device)
                 ev = torch.cuda.Event()
                 ev.record(self.stream)
             slot["result"] = (hop1, hop2, ev)
@@ -333,7 +381,8 @@ class BlockPrefetcher:
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(ev)
         for b in (hop1, hop2):               # allocated on the helper stream, consumed on this one
-            for t in (b.rowptr_d, b.col_d, b.frontier_d, b.cdeg_i, b.rdeg_i, b.rdeg_d, b.cdeg_d):
+            ts = b.tensors() if hasattr(b, "tensors") else (b.rowptr_d, b.col_d, b.frontier_d, b.cdeg_i, b.rdeg_i, b.rdeg_d, b.cdeg_d)
+            for t in ts:
                 t.record_stream(cur)
         return hop1, hop2
 

@@ -182,7 +182,7 @@ class GraphedMiniBatchStep:
         gs, dev = self.gs, self.dev
         ready = self.agg.prefetcher.take(nodes) if getattr(self.agg, "prefetcher", None) is not None else None
         hop1 = ready[0] if ready else gs._block_for(nodes, None, self.enc.adj_lists, True, dev)
-        hop2 = ready[1] if ready else gs._block_for(hop1.frontier_d, None, self.enc.adj_lists, False, dev)
+        hop2 = ready[1] if ready else gs._hop2_block(hop1.frontier_d, self.enc.adj_lists, self.enc.features, dev)
         self.agg.last_blocks = (hop1, hop2)
         assert hop1.n_rows == self.b, f"GraphedMiniBatchStep was built for {self.b}-node batches, got {hop1.n_rows}"
         e1 = int(hop1.col_d.numel())
@@ -190,9 +190,9 @@ class GraphedMiniBatchStep:
             self._alloc(max(self.u_cap, 2 * hop1.n_cols), max(self.e_cap, 2 * e1))
         table = gs._feature_table(self.enc.features)
         u = hop1.n_cols
-        ops.gather_reduce(hop1.graph("sym"), table, xmap=hop1.frontier_d, y_out=self.to_feats)
+        gs._aggregate(hop1, "sym", self.enc.features, dev, out=self.to_feats)
         self.to_feats_neigh[u:].zero_()
-        ops.gather_reduce(hop2.graph("sym"), table, xmap=hop2.frontier_d, y_out=self.to_feats_neigh[:u])
+        gs._aggregate(hop2, "sym", self.enc.features, dev, out=self.to_feats_neigh[:u])
         gm = hop1.graph("mean")
         gt = gm.T                                                            # device transpose; 1/rdeg folded into values
         self.m_rowptr.copy_(gm.rowptr)

@@ -260,6 +260,15 @@ GGAD_API int ggad_unique_sorted(const int32_t* keys, int64_t n, int64_t key_boun
 GGAD_API int ggad_block_remap(const int32_t* cols, int64_t nnz, const int32_t* uniq, int64_t n_unique,
                               int32_t* local /*[nnz]*/, int32_t* cdeg /*[n_unique]*/, ggad_stream_t stream);
 
+/* Hop block that is only GATHERED from the feature table (the hop-2 block of GCNAggregator, src/graphsage.py:335-355):
+ * neither the frontier list nor local column ids are needed -- only the batch-local column degree
+ * cdeg(u) = number of block rows containing u (src/graphsage.py:347), as the per-edge value 1/sqrt(cdeg(col[e])).
+ * counts[n_nodes] is int32 scratch (zeroed here, exact integer histogram); block_col holds GLOBAL ids from
+ * ggad_block_fill, so the gather runs straight on the table with per-edge values: no sort, no unique, no remap,
+ * no size read-back. */
+GGAD_API int ggad_block_col_weights(const int32_t* block_col, int64_t nnz, int32_t* counts, int64_t n_nodes, float* val,
+                                    ggad_stream_t stream);
+
 /* ---- synthetic graphs (C5 / S64 generator) -------------------------
  * R-MAT (a,b,c,d) edges for destination shard `shard` of `n_shards` (power of two), each shard
  * owning n_local nodes; emits keys (dst_global << 32 | src_global), dst in the shard's range,

@@ -121,6 +121,11 @@ def test_minibatch_model_matches_reference(name):
         assert np.array_equal(mask.to_dense().cpu().numpy(), ref_mask)
         assert_close(to_feats, o["to_feats"], what="to_feats")
         assert_close(to_feats_neigh, o["to_feats_neigh"][order], what="to_feats_neigh")
+        # hop 2 came through the direct form (global ids + histogram weights); the frontier-list form gives the same bits
+        assert isinstance(hop2, gs._DirectBlock)
+        hop2_list = gs._block_for(hop1.frontier_d, None, adj, False, torch.device("cuda"))
+        assert torch.equal(gs._aggregate(hop2_list, "sym", feats, None), to_feats_neigh)
+        assert hop2.n_cols == hop2_list.n_cols and np.array_equal(hop2.frontier, hop2_list.frontier)
         emb, ego, af, afn = enc(nodes, labels, True)
         assert_close(emb, o["embeds"], what="combined_all")
         assert_close(ego, o["ego"], what="ego")

@@ -151,7 +151,7 @@ def main():
         torch.cuda.synchronize()
         hop1, hop2 = agg.last_blocks
         stats.append(((time.perf_counter() - t0) * 1e3, _lib.launch_count() - l0, hop1.n_cols,
-                      int(hop1.col_d.numel()), hop2.n_cols, int(hop2.col_d.numel())))
+                      int(hop1.col_d.numel()), -1 if hasattr(hop2, "val_d") else hop2.n_cols, int(hop2.col_d.numel())))
     wall = torch.tensor([time.perf_counter() - t_all], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(wall, op=dist.ReduceOp.MAX)
