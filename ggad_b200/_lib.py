@@ -69,6 +69,7 @@ SIGNATURES = {
     "ggad_dense_matmul": (C.c_int, [_i32, _i32, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _f, _f, _i32, _i32, _vp]),
     "ggad_plan_num_tiles": (_i64, [_i64, _i64]),
     "ggad_plan_build": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
+    "ggad_plan_build_padded": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "ggad_normalize_backward": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _vp]),
     "ggad_row_inv_norm": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp]),
     "ggad_coo_keys_to_csr": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp]),

@@ -68,7 +68,7 @@ int sm_count_cached() {
 
 // implementations (gather_reduce.cu / graph_prep.cu)
 int gather_reduce_impl(const ggad_gather_desc_t* d, cudaStream_t st);
-int plan_build_impl(const int64_t*, int64_t, int64_t, int32_t*, int64_t*, cudaStream_t);
+int plan_build_impl(const int64_t*, int64_t, int64_t, int32_t*, int64_t*, cudaStream_t, int64_t n_tiles_padded = 0);
 int coo_keys_to_csr_impl(uint64_t*, int64_t, int64_t, int64_t*, int32_t*, cudaStream_t);
 int csr_transpose_impl(const int64_t*, const int32_t*, const float*, int64_t, int64_t, int64_t, int64_t*, int32_t*, float*,
                        int64_t*, cudaStream_t);
@@ -185,6 +185,11 @@ GGAD_API int64_t ggad_plan_num_tiles(int64_t n_rows, int64_t nnz) {
 GGAD_API int ggad_plan_build(const int64_t* rowptr, int64_t n_rows, int64_t nnz, int32_t* tile_row, int64_t* tile_edge,
                     ggad_stream_t stream) {
   return plan_build_impl(rowptr, n_rows, nnz, tile_row, tile_edge, (cudaStream_t)stream);
+}
+
+GGAD_API int ggad_plan_build_padded(const int64_t* rowptr, int64_t n_rows, int64_t nnz, int64_t n_tiles, int32_t* tile_row,
+                                    int64_t* tile_edge, ggad_stream_t stream) {
+  return plan_build_impl(rowptr, n_rows, nnz, tile_row, tile_edge, (cudaStream_t)stream, n_tiles);
 }
 
 GGAD_API int ggad_gather_reduce(const ggad_gather_desc_t* desc, ggad_stream_t stream) {

@@ -103,10 +103,13 @@ int gather_reduce_impl(const ggad_gather_desc_t* d, cudaStream_t st) {
 }
 
 int plan_build_impl(const int64_t* rowptr, int64_t n_rows, int64_t nnz, int32_t* tile_row, int64_t* tile_edge,
-                    cudaStream_t st) {
+                    cudaStream_t st, int64_t n_tiles_padded) {
   GGAD_REQUIRE(rowptr && tile_row && tile_edge, GGAD_ERR_INVALID, "plan_build: null pointer");
   GGAD_REQUIRE(n_rows >= 0 && nnz >= 0 && n_rows < (int64_t(1) << 31), GGAD_ERR_INVALID, "plan_build: bad sizes");
-  const int64_t n_tiles = ggad_plan_num_tiles(n_rows, nnz);
+  // a padded plan has more tiles than the CSR needs: the diagonal clamps at n_rows + nnz, so the extra tiles are empty
+  GGAD_REQUIRE(n_tiles_padded == 0 || n_tiles_padded >= ggad_plan_num_tiles(n_rows, nnz), GGAD_ERR_INVALID,
+               "plan_build: padded tile count smaller than the CSR needs");
+  const int64_t n_tiles = n_tiles_padded ? n_tiles_padded : ggad_plan_num_tiles(n_rows, nnz);
   const int64_t threads = n_tiles + 1;
   plan_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(rowptr, n_rows, nnz, n_tiles, tile_row, tile_edge);
   GGAD_CUDA_OK(cudaGetLastError());

@@ -286,8 +286,8 @@ def gcn_aggregate(g: CSRGraph, x: torch.Tensor, bias: Optional[torch.Tensor], sl
 
 class _LocalAffinity(torch.autograd.Function):
     """aff_i = (1/c_j) sum_i' R[i',j] <e^_i', e^_j>, j = subset[i]   (run.py:175-188), only for the rows
-    in ``subset``.  Forward = one gather-reduce over CSR(R^T)[subset] with col_scale 1/|e| and the dot
-    epilogue.  Backward:
+    in ``subset``.  Forward = row normalisation + one gather-reduce of e^ over CSR(R^T)[subset] with the dot
+    epilogue.  Backward, first term through the transposed row-subset CSR:
         de^_k = sum_j R[k,j] (g_j/c_j) e^_j  +  [k in subset] (g_k/c_k) sum_i' R[i',k] e^_i'
         de_k  = (de^_k - e^_k <e^_k, de^_k>) / |e_k|
     """
@@ -298,22 +298,25 @@ class _LocalAffinity(torch.autograd.Function):
         inv = torch.empty(n, dtype=torch.float32, device=emb.device)
         with torch.cuda.device(emb.device):
             check(lib().ggad_row_inv_norm(ptr(emb), emb.stride(0), n, d, ptr(inv), None, stream_ptr(emb.device)))
-        dot_scale = inv[subset.long()] * r_inv_sub
-        r = gather_reduce(g_rt_sub, emb, col_scale=inv, dot_mat=emb, dot_rows=subset, dot_scale=dot_scale,
-                          use_graph_scales=False)
-        ctx.g_r = g_r
-        ctx.save_for_backward(emb, inv, r["y"], subset, r_inv_sub)
+        # e^ = e / |e| once (N x d elementwise), so the gather runs in the plain per-edge-value mode instead of the
+        # general one (a col_scale lookup per edge): aff_j = r_inv_j <sum_i R[i,j] e^_i , e^_j>
+        ehat = emb * inv.unsqueeze(1)
+        r = gather_reduce(g_rt_sub, ehat, dot_mat=ehat, dot_rows=subset, dot_scale=r_inv_sub, use_graph_scales=False)
+        ctx.g_sub = g_rt_sub
+        ctx.save_for_backward(emb, inv, ehat, r["y"], subset, r_inv_sub)
         return r["dot"]
 
     @staticmethod
     def backward(ctx, g_aff):
-        emb, inv, acc, subset, r_inv_sub = ctx.saved_tensors
+        emb, inv, ehat, acc, subset, r_inv_sub = ctx.saved_tensors
         n, d = emb.shape
         gamma = g_aff * r_inv_sub                                  # g_j / c_j on the subset
-        cs = torch.zeros(n, dtype=torch.float32, device=emb.device)
-        cs[subset.long()] = gamma * inv[subset.long()]             # col_scale: gamma_j / |e_j|, 0 elsewhere (skipped)
-        de = gather_reduce(ctx.g_r, emb, col_scale=cs, use_graph_scales=False)["y"]
-        de.index_add_(0, subset.long(), acc * gamma.unsqueeze(1))
+        # first term: sum_{j in subset} R[k,j] gamma_j e^_j  =  (R^T[subset,:])^T @ (gamma * e^[subset]) -- a plain gather
+        # over the |subset|/N fraction of the edges (the transposed row-subset CSR, built once and cached), instead of
+        # a masked pass over all of R
+        xs = ehat[subset.long()] * gamma.unsqueeze(1)
+        de = gather_reduce(ctx.g_sub.T, xs, use_graph_scales=False)["y"]
+        de.index_add_(0, subset.long(), acc * gamma.unsqueeze(1))  # second term, only on the subset rows
         with torch.cuda.device(emb.device):
             check(lib().ggad_normalize_backward(ptr(emb), emb.stride(0), ptr(inv), ptr(de), de.stride(0), n, d,
                                                 stream_ptr(emb.device)))

@@ -13,6 +13,7 @@ from typing import Optional, Sequence
 
 import torch
 
+from ._lib import check, lib, ptr, stream_ptr
 from .graph import CSRGraph
 from .losses import ggad_loss
 from .model import Model, as_graph
@@ -124,9 +125,15 @@ class GraphedMiniBatchStep:
         # ego-mean operator M = mask / rdeg over the hop-1 block [B, |U|] and its transpose [u_cap, B] (per-edge values)
         self.m_rowptr, self.m_col, self.m_rs = z64(b + 1), z32(self.e_cap), torch.zeros(b, device=dev)
         self.t_rowptr, self.t_col, self.t_val = z64(self.u_cap + 1), z32(self.e_cap), torch.zeros(self.e_cap, device=dev)
-        g = CSRGraph(self.m_rowptr, self.m_col, None, b, self.u_cap, row_scale=self.m_rs, use_plan=False)
-        gt = CSRGraph(self.t_rowptr, self.t_col, self.t_val, self.u_cap, b, use_plan=False)
+        # both run the merge-path tiled kernel (a hub among the batch nodes is one long row) on a plan PADDED to the
+        # capacity: the captured launch has a fixed tile count, the plan arrays are refreshed per batch (_load)
+        g = CSRGraph(self.m_rowptr, self.m_col, None, b, self.u_cap, row_scale=self.m_rs, use_plan=True)
+        gt = CSRGraph(self.t_rowptr, self.t_col, self.t_val, self.u_cap, b, use_plan=True)
+        for gg in (g, gt):
+            nt = int(lib().ggad_plan_num_tiles(gg.n_rows, self.e_cap))
+            gg._plan = (torch.zeros(nt + 1, dtype=torch.int32, device=dev), torch.zeros(nt + 1, dtype=torch.int64, device=dev), nt)
         g._T, gt._T = gt, g
+        self.g, self.gt = g, gt
         outer = self
 
         class _Mask:                       # what loss_from_aggregates calls .mm on
@@ -202,6 +209,10 @@ class GraphedMiniBatchStep:
         self.t_rowptr[u + 1:].fill_(e1)                                      # padding rows are empty
         self.t_col[:e1].copy_(gt.col)
         self.t_val[:e1].copy_(gt.val)
+        with torch.cuda.device(dev):
+            for gg in (self.g, self.gt):
+                tr, te, nt = gg._plan
+                check(lib().ggad_plan_build_padded(ptr(gg.rowptr), gg.n_rows, e1, nt, ptr(tr), ptr(te), stream_ptr(dev)))
         self.lab.copy_(labels.reshape(-1), non_blocking=True)
 
     def step(self, nodes, labels):

@@ -199,6 +199,13 @@ GGAD_API int ggad_dense_matmul(int32_t trans_a, int32_t trans_b, int64_t m, int6
                                const float* b, int64_t ldb, float* c, int64_t ldc, float alpha, float beta, int32_t relu,
                                int32_t path, ggad_stream_t stream);
 
+/* Plan with a FIXED tile count n_tiles >= ggad_plan_num_tiles(n_rows, nnz) (the extra tiles are empty): a CSR whose arrays
+ * are static buffers padded to a capacity -- so that a gather launch captured in a CUDA graph with the capacity as its
+ * nnz keeps working when the real edge count changes from replay to replay; only this (tiny) plan kernel is re-run.
+ * Used by the graphed mini-batch step for the ego-mean operator of src/graphsage.py:421 and its transpose. */
+GGAD_API int ggad_plan_build_padded(const int64_t* rowptr, int64_t n_rows, int64_t nnz, int64_t n_tiles, int32_t* tile_row,
+                                    int64_t* tile_edge, ggad_stream_t stream);
+
 /* ---- K4: backward helper of the local-affinity cosine ---------------------------
  * de_k = ( g_k - e^_k <e^_k, g_k> ) * inv_norm_k   with e^_k = e_k * inv_norm_k, in place on g.
  * (autograd of run.py:177-180.) */
