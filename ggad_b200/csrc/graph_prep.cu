@@ -101,12 +101,15 @@ __global__ void block_degree_kernel(const int64_t* __restrict__ rowptr, const in
   deg[i] = d + ((add_self && !has_self) ? 1 : 0);
 }
 
-// one warp per block row: copy the neighbor slice, append the node itself if it was not a neighbor
-__global__ void block_fill_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n_nodes,
-                                  const int32_t* __restrict__ nodes, int64_t n_batch, int add_self,
-                                  const int64_t* __restrict__ block_rowptr, int32_t* __restrict__ out) {
-  const int64_t w = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+// one 128-thread CTA per block row (a frontier holds hub rows with 10^5 neighbors: one warp per row made the launch
+// as long as its longest row): copy the neighbor slice, append the node itself if it was not a neighbor
+constexpr int kFillThreads = 128;
+__global__ void __launch_bounds__(kFillThreads) block_fill_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                                  int64_t n_nodes, const int32_t* __restrict__ nodes, int64_t n_batch,
+                                                                  int add_self, const int64_t* __restrict__ block_rowptr,
+                                                                  int32_t* __restrict__ out) {
+  const int64_t w = blockIdx.x;
+  const int lane = threadIdx.x;
   if (w >= n_batch) return;
   const int64_t v = nodes[w];
   const int64_t o = block_rowptr[w], total = block_rowptr[w + 1] - o;
@@ -115,7 +118,7 @@ __global__ void block_fill_kernel(const int64_t* __restrict__ rowptr, const int3
     s = rowptr[v];
     n = rowptr[v + 1] - s;
   }
-  for (int64_t t = lane; t < n; t += 32) out[o + t] = col[s + t];
+  for (int64_t t = lane; t < n; t += kFillThreads) out[o + t] = col[s + t];
   if (add_self && total > n && lane == 0) out[o + n] = int32_t(v);
 }
 
@@ -417,8 +420,9 @@ int block_fill_impl(const int64_t* rowptr, const int32_t* col, int64_t n_nodes, 
                     int add_self, const int64_t* block_rowptr, int32_t* block_col, cudaStream_t st) {
   GGAD_REQUIRE(rowptr && (nodes || n_batch == 0) && block_rowptr && n_batch >= 0, GGAD_ERR_INVALID, "block_fill: bad arguments");
   if (n_batch == 0) return GGAD_OK;
-  block_fill_kernel<<<blocks_for(n_batch * 32), 256, 0, st>>>(rowptr, col, n_nodes, nodes, n_batch, add_self, block_rowptr,
-                                                              block_col);
+  GGAD_REQUIRE(n_batch < (int64_t(1) << 31), GGAD_ERR_UNSUPPORTED, "block_fill: too many block rows");
+  block_fill_kernel<<<(unsigned)n_batch, kFillThreads, 0, st>>>(rowptr, col, n_nodes, nodes, n_batch, add_self, block_rowptr,
+                                                                block_col);
   GGAD_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return GGAD_OK;
