@@ -95,10 +95,10 @@ __device__ __forceinline__ void store_y(const GatherArgs& a, int64_t r, int ch, 
 // Full per-row epilogue (bias / activation / z / sumsq / dot).  It is large, so kernels that use it keep the
 // number of inlined copies at two (rolled boundary path below); a non-inlined call was measured slower
 // (register spills around the call sites), 17 inlined copies 2x slower (instruction cache).
-template <int G, int CH, bool PEER, bool PRESCALED = false>
+template <int G, int CH, bool PEER>
 __device__ __forceinline__ void finish_row_full(const GatherArgs& a, int64_t r, const float4* acc, int gl, unsigned gmask) {
   const int V = a.d >> 2;
-  const float rs = (!PRESCALED && a.row_scale) ? __ldg(a.row_scale + r) : 1.f;
+  const float rs = a.row_scale ? __ldg(a.row_scale + r) : 1.f;
   const bool want_dot = a.dot_out != nullptr;
   const bool want_ss = a.sumsq != nullptr;
   const float4* dm = nullptr;
@@ -156,10 +156,8 @@ __device__ __forceinline__ void finish_row_full(const GatherArgs& a, int64_t r, 
 //             model.py:29-35.  Small enough to be inlined at every row end like the plain one (bias comes from shared
 //             memory, the slope from a register), so the launch keeps the unrolled gather loop.
 //   2 full    additionally |y|^2 and the dot epilogue (group shuffles); rolled boundary walk, three inlined copies.
-//   3 deferred  the gather loop is the plain one (y = row_scale * acc at every row end); after its loop every lane
-//             group re-reads the rows it finished (its own stores: same thread, same address; L2 hits, two rows in
-//             flight) and applies the full epilogue in ONE rolled loop.  Costs one extra L2 read of y but keeps the
-//             hot loop identical to the plain kernel whatever the epilogue asks for.  Needs the y output.
+//   (a fourth kind -- plain loop, then every lane group re-reads its rows from L2 and applies the full epilogue in one
+//   rolled loop -- was measured 26 % slower than kind 1 on the GCN-layer launch and removed: profiles/r02a_variants_S64_deferred.txt)
 struct EpiRegs {
   const float* s_bias;  // shared memory, d floats (zeros when there is no bias)
   float slope;
@@ -203,7 +201,7 @@ __device__ __forceinline__ void finish_row(const GatherArgs& a, int64_t r, const
     return;
   }
   const float rs = a.row_scale ? __ldg(a.row_scale + r) : 1.f;
-  if (EPI == 0 || EPI == 3) {  // plain SpMM: y = row_scale * acc (EPI 3: the epilogue follows in post_rows)
+  if (EPI == 0) {  // plain SpMM: y = row_scale * acc, nothing else requested
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       const int ch = gl + G * j;
@@ -370,29 +368,6 @@ __device__ __forceinline__ void push_group_rows(const GatherArgs& a, int64_t ra,
       if (n0 && ch < V) send(r * a.ldy + int64_t(ch) * 4, n0, v0[j]);
       if (n1 && ch < V) send((r + 1) * a.ldy + int64_t(ch) * 4, n1, v1[j]);
     }
-  }
-}
-
-// Deferred epilogue (EPI 3): rows [ra, rb) were finished by THIS lane group as y = row_scale * acc; every lane
-// re-reads exactly the chunks it stored itself, two rows in flight, and runs the full epilogue on them.
-template <int G, int CH, bool PEER>
-__device__ __forceinline__ void post_rows(const GatherArgs& a, int64_t ra, int64_t rb, int gl, unsigned gmask) {
-  if (ra >= rb) return;
-  const int V = a.d >> 2;
-  auto load_row = [&](int64_t r, float4 (&v)[CH]) {
-#pragma unroll
-    for (int j = 0; j < CH; ++j) {
-      const int ch = gl + G * j;
-      v[j] = (ch < V) ? __ldcg(reinterpret_cast<const float4*>(a.y + r * a.ldy) + ch) : f4_zero();
-    }
-  };
-  float4 cur[CH], nxt[CH];
-  load_row(ra, cur);
-  for (int64_t r = ra; r < rb; ++r) {   // one epilogue copy; the next row's load is in flight while this one finishes
-    if (r + 1 < rb) load_row(r + 1, nxt);
-    finish_row_full<G, CH, PEER, true>(a, r, cur, gl, gmask);
-#pragma unroll
-    for (int j = 0; j < CH; ++j) cur[j] = nxt[j];
   }
 }
 
@@ -717,7 +692,6 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
       flag |= 2;
     }
     if (gl == 0) s_flag[g] = flag;
-    if constexpr (EPI == 3) post_rows<G, CH, false>(a, r0 + i1 + (head0 ? 1 : 0), r0 + i2, gl, gmask);
 #if GGAD_PUSH_PER_GROUP
     if constexpr (PEER) push_group_rows<G, CH>(a, r0 + i1 + (head0 ? 1 : 0), r0 + i2, gl);
 #endif
@@ -743,7 +717,7 @@ __global__ void __launch_bounds__(kThreads, (CH == 1) ? 4 : ((CH == 2) ? 3 : 2))
           for (int j = 0; j < CH; ++j)
             if (gl + G * j < V) reinterpret_cast<float4*>(ws_head)[gl + G * j] = chain[j];
         } else {
-          finish_row<G, CH, (EPI == 3) ? 2 : EPI, (GGAD_PUSH_PER_GROUP != 0) && PEER>(a, r0 + row, chain, gl, gmask, ep);
+          finish_row<G, CH, EPI, (GGAD_PUSH_PER_GROUP != 0) && PEER>(a, r0 + row, chain, gl, gmask, ep);
         }
 #pragma unroll
         for (int j = 0; j < CH; ++j) chain[j] = f4_zero();
@@ -847,8 +821,6 @@ int launch_variant(const GatherArgs& a, cudaStream_t st, int sm_count) {
     static const bool force_full = getenv("GGAD_FORCE_FULL_EPI") != nullptr;   // A/B knob (profiling only)
     const int epi = (a.sumsq || a.dot_out || (!a.y && !a.y_mc) || (force_full && (a.bias || a.prelu_slope || a.relu || a.z)))
                         ? 2 : ((a.bias || a.prelu_slope || a.relu || a.z) ? 1 : 0);
-    static const bool deferred = getenv("GGAD_EPI_DEFERRED") != nullptr;        // A/B knob: epilogue kind 3
-    if (deferred && epi != 0 && a.y) return peer ? launch_mode<G, CH, 3, true>(a, st) : launch_mode<G, CH, 3, false>(a, st);
     if (peer) {
       if (epi == 2) return launch_mode<G, CH, 2, true>(a, st);
       return epi == 1 ? launch_mode<G, CH, 1, true>(a, st) : launch_mode<G, CH, 0, true>(a, st);
