@@ -421,7 +421,8 @@ def native(args):
                 ops.gather_reduce(fwd, x, y_out=rep.local_rows, y_peers=peer_ptrs, peer_need=need, chase=True,
                                   chase_ctas=args.chase_ctas, y_multicast=mc_ptr, mc_min_peers=args.mc_min)
             elif exchange == "halo":
-                ops.gather_reduce(fwd, x, y_out=rep.local_rows, y_peers=peer_ptrs, peer_need=need)
+                ops.gather_reduce(fwd, x, y_out=rep.local_rows, y_peers=peer_ptrs, peer_need=need,
+                                  y_multicast=mc_ptr, mc_min_peers=args.mc_min)
             else:
                 ops.gather_reduce(fwd, x, y_out=rep.local_rows, y_peers=peer_ptrs, peer_need=need)
             if ev:
@@ -863,7 +864,7 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: wall budget of the timed steps (s)")
     ap.add_argument("--chase-ctas", type=int, default=0, help="exchange=chase: CTAs of the chase kernel (0 = library default)")
     ap.add_argument("--mc-min", type=int, default=0,
-                    help="exchange=chase: rows needed by at least this many peers go once through the NVSwitch multicast "
+                    help="exchange=halo|chase: rows needed by at least this many peers go once through the NVSwitch multicast "
                          "address instead of one unicast store per peer (0 = never)")
     ap.add_argument("--verify-rows", type=int, default=4096, help="rows of Y and of dX recomputed on the CPU after the timed region")
     ap.add_argument("--exchange", default="halo", choices=["chase", "halo", "fused", "multicast", "nccl"],

@@ -57,6 +57,7 @@ struct GatherArgs {
   const uint32_t* peer_need;
   int32_t* tile_done;   // chase mode: tile k publishes tile_done[k] = tile_epoch instead of pushing its rows
   int32_t tile_epoch;
+  int32_t mc_min;       // hybrid exchange: rows needed by >= mc_min peers take the multicast address (0: y_mc takes all)
 };
 
 constexpr int kThreads = 256;
@@ -80,15 +81,17 @@ __device__ __forceinline__ void store_y(const GatherArgs& a, int64_t r, int ch, 
     return;
   }
   if (a.y) stg_cs_f4(reinterpret_cast<float4*>(a.y + off), v);
-  // halo exchange: only the peers whose next pass gathers this row receive it
-  const uint32_t need = a.peer_need ? __ldg(a.peer_need + r) : 0xffffffffu;
-  for (int p = 0; p < a.n_peer; ++p)
-    if ((need >> p) & 1u) stg_peer_f4(reinterpret_cast<float4*>(a.y_peer[p] + off), v);
-  if (a.y_mc) {
+  // halo exchange: only the peers whose next pass gathers this row receive it; a row that many peers need goes ONCE
+  // through the NVSwitch multicast address instead (hybrid: mc_min > 0), every row does when only y_mc is given
+  const uint32_t need = (a.peer_need ? __ldg(a.peer_need + r) : 0xffffffffu) & ((1u << a.n_peer) - 1u);
+  if (a.y_mc && (a.mc_min <= 0 || __popc(need) >= a.mc_min)) {
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.y_mc + off), "f"(v.x), "f"(v.y),
                  "f"(v.z), "f"(v.w)
                  : "memory");
+    return;
   }
+  for (int p = 0; p < a.n_peer; ++p)
+    if ((need >> p) & 1u) stg_peer_f4(reinterpret_cast<float4*>(a.y_peer[p] + off), v);
 }
 
 // Per-row epilogue; executed convergently by the G lanes of one group.
@@ -283,13 +286,14 @@ __device__ __forceinline__ void push_rows(const GatherArgs& a, int64_t ra, int64
   const int V = a.d >> 2;
   const uint32_t all = (1u << a.n_peer) - 1u;
   const int nrow = int(rb - ra);
-  const bool mc = a.y_mc != nullptr;
+  const bool mc_all = a.y_mc != nullptr && a.mc_min <= 0;       // pure multicast: every row, once
+  const bool mc_some = a.y_mc != nullptr && a.mc_min > 0;       // hybrid: rows that >= mc_min peers need
   for (int j = tid; j < nrow; j += nthreads)
-    s_need[j] = mc ? 1u : ((a.peer_need ? __ldg(a.peer_need + ra + j) : 0xffffffffu) & all);
+    s_need[j] = mc_all ? 1u : ((a.peer_need ? __ldg(a.peer_need + ra + j) : 0xffffffffu) & all);
   __syncthreads();
   const int total = nrow * V;
   auto send = [&](int64_t off, uint32_t need, const float4& v) {
-    if (mc) {
+    if (mc_all || (mc_some && __popc(need) >= a.mc_min)) {
       asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.y_mc + off), "f"(v.x), "f"(v.y),
                    "f"(v.z), "f"(v.w)
                    : "memory");

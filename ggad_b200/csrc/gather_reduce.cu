@@ -91,11 +91,14 @@ int gather_reduce_impl(const ggad_gather_desc_t* d, cudaStream_t st) {
   a.peer_need = d->peer_need;
   a.tile_done = d->tile_done;
   a.tile_epoch = d->tile_epoch;
+  a.mc_min = d->mc_min_peers;
   GGAD_REQUIRE(!a.tile_done || (d->tile_row && d->y && !a.y_mc), GGAD_ERR_INVALID,
                "gather_reduce: tile_done (chase mode) needs the merge-path plan and y, and excludes y_multicast");
   GGAD_REQUIRE((d->n_peer == 0 && !a.y_mc) || d->y, GGAD_ERR_INVALID, "gather_reduce: the fused exchange needs the local y");
-  GGAD_REQUIRE(!a.peer_need || (d->n_peer > 0 && !a.y_mc), GGAD_ERR_INVALID,
-               "gather_reduce: peer_need needs y_peer[] and excludes y_multicast");
+  GGAD_REQUIRE(!a.peer_need || (d->n_peer > 0 && (!a.y_mc || d->mc_min_peers > 0)), GGAD_ERR_INVALID,
+               "gather_reduce: peer_need needs y_peer[]; with y_multicast it needs mc_min_peers > 0 (hybrid exchange)");
+  GGAD_REQUIRE(d->mc_min_peers >= 0 && (d->mc_min_peers == 0 || (a.y_mc && d->n_peer > 0)), GGAD_ERR_INVALID,
+               "gather_reduce: mc_min_peers needs both y_multicast and y_peer[]");
   GGAD_REQUIRE(aligned16(a.y_mc), GGAD_ERR_ALIGN, "gather_reduce: y_multicast not 16-byte aligned");
   const int sms = sm_count_cached();
   if (sms <= 0) return GGAD_ERR_CUDA;

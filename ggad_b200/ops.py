@@ -91,6 +91,8 @@ def gather_reduce(g: CSRGraph, x: torch.Tensor, *, xmap: Optional[torch.Tensor] 
             desc.peer_need = ptr(peer_need)
     if y_multicast and not chase:
         desc.y_multicast = int(y_multicast)
+        if y_peers and mc_min_peers > 0:          # hybrid: rows many peers need take the multicast address
+            desc.mc_min_peers = int(mc_min_peers)
     plan = g.plan
     if plan is not None:
         ws = g.workspace(d)

@@ -135,6 +135,11 @@ typedef struct ggad_gather_desc {
    * its tile finished are in y, and a concurrently running ggad_halo_chase moves them over NVLink from a few SMs
    * of its own.  Rows cut by tile boundaries are still pushed by the fix-up kernel of this launch. */
   int32_t* tile_done;
+  /* hybrid exchange: with y_peer[] AND y_multicast given, a row whose mask has at least mc_min_peers bits set is
+   * stored once through the multicast address (it lands in every rank's replica) instead of once per peer that
+   * needs it; 0 = off (y_multicast alone then means: every row through the multicast address). */
+  int32_t mc_min_peers;
+  int32_t reserved2;
 } ggad_gather_desc_t;
 
 GGAD_API int ggad_gather_reduce(const ggad_gather_desc_t* desc, ggad_stream_t stream);

@@ -65,3 +65,28 @@ def test_clock_sampler_degrades_without_nvml():
     s.mark_end()
     out = s.stop()
     assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+def test_in_bench_row_verification_catches_a_wrong_row():
+    """bench.verify_sampled_rows (the parity check bench.py runs after the timed region at the benchmark's own size):
+    passes on a correct fp32 SpMM result, fails on a single perturbed row; works on any object with CSR attributes."""
+    import types
+    import scipy.sparse as sp
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    n, d = 20000, 16
+    rp, col = bench.rmat_csr_numpy(n, 300000, 3)
+    deg = np.diff(rp)
+    rng = np.random.default_rng(0)
+    g = types.SimpleNamespace(rowptr=torch.from_numpy(rp), col=torch.from_numpy(col), val=torch.from_numpy(rng.random(len(col)).astype(np.float32)),
+                              n_rows=n, row_scale=torch.from_numpy(np.where(deg > 0, 1.0 / np.maximum(deg, 1), 0).astype(np.float32)),
+                              col_scale=torch.from_numpy(rng.random(n).astype(np.float32)), device=torch.device("cpu"))
+    x = torch.from_numpy(rng.standard_normal((n, d)).astype(np.float32))
+    a = sp.csr_matrix((g.val.numpy() * g.col_scale.numpy()[col], col, rp), shape=(n, n))
+    y = torch.from_numpy((sp.diags(g.row_scale.numpy()) @ a @ x.numpy()).astype(np.float32))
+    rows, worst = bench.verify_sampled_rows(g, x, y, 1024, 0)
+    assert rows > 900 and worst < 0.5
+    hub = int(np.argmax(deg))                       # the highest-degree row is always in the sample
+    y[hub] += 1e-2 * (1.0 + y[hub].abs())
+    assert bench.verify_sampled_rows(g, x, y, 1024, 0)[1] > 1.0

@@ -76,11 +76,12 @@ def _worker(rank, world, port, q):
     rep.barrier(1)
     # chase exchange (tile-done flags + ggad_halo_chase on a second stream), plain and with the hybrid rule "rows that
     # >= 1 peer needs go once through the multicast address": same contract as the halo push above
-    for mc_min in ([0, 1] if rep.multicast_ptr else [0]):
+    # (the hybrid rule also exists in the in-kernel end-of-tile push: chase=False, mc_min=1)
+    for chase_, mc_min in ([(True, 0), (True, 1), (False, 1)] if rep.multicast_ptr else [(True, 0)]):
         rep.barrier(0)
         rep.buf.fill_(float("nan"))
         rep.barrier(1)
-        ops.gather_reduce(fwd, x, y_out=rep.local_rows, y_peers=rep.peer_row_ptrs, peer_need=need, chase=True,
+        ops.gather_reduce(fwd, x, y_out=rep.local_rows, y_peers=rep.peer_row_ptrs, peer_need=need, chase=chase_,
                           y_multicast=rep.multicast_row_ptr if mc_min else None, mc_min_peers=mc_min)
         rep.barrier(0)
         chase_ok = torch.equal(rep.buf[mine], y[mine])
