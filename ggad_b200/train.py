@@ -213,6 +213,8 @@ class GraphedMiniBatchStep:
             for gg in (self.g, self.gt):
                 tr, te, nt = gg._plan
                 check(lib().ggad_plan_build_padded(ptr(gg.rowptr), gg.n_rows, e1, nt, ptr(tr), ptr(te), stream_ptr(dev)))
+        if not labels.is_cuda and bool(((labels != 0) & (labels != 1)).any()):
+            raise RuntimeError("GraphedMiniBatchStep: labels must be 0 / 1 (the static-shape loss; use GCN.loss_reference_path otherwise)")
         self.lab.copy_(labels.reshape(-1), non_blocking=True)
 
     def step(self, nodes, labels):
