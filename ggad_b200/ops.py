@@ -169,6 +169,12 @@ def dense_matmul(a: torch.Tensor, b: torch.Tensor, *, trans_a: bool = False, tra
         out = buf[:, :n]
     else:
         assert out.shape == (m, n) and out.stride(1) == 1 and out.is_cuda and out.dtype == torch.float32
+    if k == 0 or m == 0 or n == 0:          # nothing to multiply: C = act(beta * C)
+        if beta == 0.0:
+            out.zero_()
+        else:
+            out.mul_(beta)
+        return torch.relu_(out) if relu else out
     with torch.cuda.device(a.device):
         check(lib().ggad_dense_matmul(int(trans_a), int(trans_b), m, n, k, ptr(a), a.stride(0), ptr(b), b.stride(0),
                                       ptr(out), out.stride(0), float(alpha), float(beta), int(relu), int(path),

@@ -576,3 +576,56 @@ def test_linear_autograd_matches_torch():
     for got, ref, what in ((y[0], y64, "y"), (xd.grad, x64.grad, "dx"), (wd.grad, w64.grad, "dw")):
         err = (got.detach().double().cpu() - ref.detach()).abs().max().item()
         assert err <= 1e-5 * ref.detach().abs().max().item(), f"{what}: {err:.3e}"
+
+
+# ------------------------------------------------------------------------------------------
+# edge cases: empty / ragged inputs, maximum width, degenerate GEMMs
+# ------------------------------------------------------------------------------------------
+def test_edge_cases_empty_ragged_and_maximum_width():
+    _, _lib, graph, ops, _ = _mods()
+    # no rows at all, rows without any edge, one edge only -- with and without a plan
+    z64 = np.zeros(1, np.int64)
+    for use_plan in (False, True):
+        g0 = graph.CSRGraph.from_arrays(z64, np.zeros(0, np.int32), None, 0, 5, use_plan=use_plan)
+        assert ops.gather_reduce(g0, torch.randn(5, 8).cuda())["y"].shape == (0, 8)
+        ge = graph.CSRGraph.from_arrays(np.zeros(4001, np.int64), np.zeros(0, np.int32), None, 4000, 7, use_plan=use_plan)
+        r = ops.gather_reduce(ge, torch.randn(7, 8).cuda(), bias=torch.ones(8).cuda(), want_sumsq=True)
+        assert bool((r["y"] == 1).all()) and bool((r["sumsq"] == 8).all())          # empty rows: y = bias
+    # the widest row the library takes (GGAD_MAX_WIDTH = 768 floats) and one float4 (d = 4), ragged degrees with a hub
+    for d in (_lib.GGAD_MAX_WIDTH, 4):
+        rowptr, col, val = make_csr(3000, 2000, 6.0, seed=d, hub=5000)
+        g = graph.CSRGraph.from_arrays(rowptr, col, val, 3000, 2000, use_plan=True)
+        x = torch.randn(2000, d)
+        assert_close(ops.gather_reduce(g, x.cuda())["y"], oracle.spmm_csr(rowptr, col, val, x), rtol=RTOL, atol=3e-4, what=f"d={d}")
+    with pytest.raises(RuntimeError, match="width"):
+        ops.gather_reduce(g, torch.randn(2000, _lib.GGAD_MAX_WIDTH + 4).cuda())
+    with pytest.raises(RuntimeError, match="columns"):                              # operand shorter than the graph's columns
+        ops.gather_reduce(g, torch.randn(1999, 8).cuda())
+    # one row that is the whole matrix: 300 k edges over 147 tiles, finished by the fix-up kernel
+    n_e = 300_000
+    rng = np.random.default_rng(0)
+    rp = np.array([0, 0, n_e, n_e], np.int64)
+    c1 = rng.integers(0, 1000, n_e).astype(np.int32)
+    g1 = graph.CSRGraph.from_arrays(rp, c1, None, 3, 1000, use_plan=True)
+    x = torch.randn(1000, 16)
+    ref = oracle.spmm_csr(rp, c1, None, x)
+    assert_close(ops.gather_reduce(g1, x.cuda())["y"], ref, rtol=RTOL, atol=2e-3 * float(ref.abs().max()) * 1e-1, what="single giant row")
+    # degenerate projections: no rows, no inner dimension, a single output column
+    assert ops.dense_matmul(torch.randn(0, 8).cuda(), torch.randn(4, 8).cuda(), trans_b=True).shape == (0, 4)
+    assert bool((ops.dense_matmul(torch.randn(5, 0).cuda(), torch.randn(4, 0).cuda(), trans_b=True) == 0).all())
+    a1, b1 = torch.randn(300, 75), torch.randn(1, 75)
+    assert_close(ops.linear(a1.cuda(), b1.cuda()), a1 @ b1.t(), rtol=1e-4, atol=1e-5, what="h/4 -> 1 score layer")
+
+
+def test_layerwise_inference_empty_and_single_node():
+    from ggad_b200 import evaluate, graphsage as gs, synth
+    adj = synth.rmat_adjacency(5000, 40000, seed=1, device="cuda")
+    feats = torch.nn.Embedding(5000, 17)
+    feats.weight = torch.nn.Parameter(torch.rand(5000, 17), requires_grad=False)
+    feats = feats.cuda()
+    enc = gs.GCNEncoder(feats, 17, 16, adj, gs.GCNAggregator(feats, cuda=True), gcn=True, cuda=True)
+    model = gs.GCN(2, enc).cuda()
+    assert evaluate.to_prob_all(model, [], 200).numel() == 0
+    one = evaluate.to_prob_all(model, [17], 200)
+    with torch.no_grad():
+        assert_close(one, model.to_prob([17], None)[:, 0], rtol=1e-6, atol=1e-7, what="single node")
