@@ -125,7 +125,8 @@ typedef struct ggad_gather_desc {
   float* y_peer[7];
   int32_t n_peer;
   int32_t tile_epoch; /* chase mode (tile_done below): value published per finished tile, != the buffer's old contents */
-  float* y_multicast; /* NULL or multicast address covering all ranks (used instead of y_peer) */
+  float* y_multicast; /* NULL or multicast address covering all ranks: alone = every row once through the switch;
+                         together with y_peer[] + mc_min_peers (below) = only the rows that many peers need */
   /* halo exchange: NULL (every row goes to every peer) or [n_rows] bit masks -- bit p set means y_peer[p]
    * gathers row r in its next pass (the row is a column of that peer's CSR shard), so only those rows
    * cross NVLink.  Rows a peer does not need are left untouched in its replica. */
