@@ -359,6 +359,10 @@ def native(args):
         else:
             row_cost = float(args.row_cost)
             br, bwd = build_bwd(row_cost)
+    if args.edge_order == "hot-first":
+        # plan-time re-ordering of every row's edges by column popularity (CSRGraph.reorder_edges_hot_first)
+        fwd = fwd.reorder_edges_hot_first()
+        bwd = bwd.reorder_edges_hot_first()
     for g in (fwd, bwd):
         g.plan
     torch.cuda.synchronize()
@@ -565,7 +569,7 @@ def native(args):
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (R-MAT %s, on-device)" % (args.rmat or "0.57/0.19/0.19/0.05"),
             "config": {"workload": args.workload, "nodes_per_gpu": n_local, "edges_per_gpu": m_local, "width": d,
-                       "global_nodes": n_glob, "global_edges": total_edges, "aggregation": "mean (row_scale = 1/deg)",
+                       "global_nodes": n_glob, "global_edges": total_edges, "aggregation": "mean (row_scale = 1/deg)", "edge_order": args.edge_order,
                        "l2": "inputs larger than L2 (no flush)" if n_glob * d * 4 > 2e8 else "L2-resident operand (no flush)",
                        "parallelism": f"dst-node-range x{world}, exchange={exchange}", "graph_build_s": round(t_build, 2),
                        "halo_rows_sent_frac": halo_frac, "bwd_ranges": [list(map(int, r)) for r in br], "bwd_row_cost": row_cost,
@@ -878,6 +882,9 @@ def main():
                          "a timed trial split (profile-guided)")
     ap.add_argument("--peer-debug", default=None, choices=["zero_mask", "local_peers"],
                     help="diagnostics only (results are NOT exchanged): isolate the cost of the peer stores")
+    ap.add_argument("--edge-order", default="column", choices=["column", "hot-first"],
+                    help="order of the edges inside a CSR row: by column id (as a CSR build leaves them) or most popular "
+                         "column first (homogeneous L2-hit / DRAM-miss batches)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-slots", type=int, default=3, help="N=1 end-to-end leg: pipeline depth (streams with their own scratch)")
     ap.add_argument("--no-cpu", action="store_true")

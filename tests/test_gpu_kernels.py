@@ -629,3 +629,24 @@ def test_layerwise_inference_empty_and_single_node():
     one = evaluate.to_prob_all(model, [17], 200)
     with torch.no_grad():
         assert_close(one, model.to_prob([17], None)[:, 0], rtol=1e-6, atol=1e-7, what="single node")
+
+
+def test_hot_first_edge_order_is_the_same_operator():
+    """CSRGraph.reorder_edges_hot_first permutes the edges inside every row (most popular column first): same rowptr,
+    same multiset of (column, value) per row -> same scipy operator exactly, same SpMM result up to the fp32 summation
+    order (checked against the oracle), and the most popular column of a row now comes first."""
+    _, _, graph, ops, _ = _mods()
+    rowptr, col, val = make_csr(5000, 3000, 12.0, seed=8, hub=6000)
+    col[: len(col) // 3] = col[: len(col) // 3] % 50                      # a popular set of columns
+    g = graph.CSRGraph.from_arrays(rowptr, col, val, 5000, 3000, use_plan=True)
+    h = g.reorder_edges_hot_first()
+    assert torch.equal(h.rowptr, g.rowptr)
+    a, b = g.to_scipy(), h.to_scipy()
+    a.sum_duplicates(); b.sum_duplicates()
+    assert abs(a - b).max() < 1e-6
+    x = torch.randn(3000, 64)
+    assert_close(ops.gather_reduce(h, x.cuda())["y"], oracle.spmm_csr(rowptr, col, val, x), rtol=RTOL, atol=3e-4, what="hot-first order")
+    pop = torch.bincount(g.col, minlength=3000)
+    r = 4000
+    seg = h.col[int(h.rowptr[r]):int(h.rowptr[r + 1])].long()
+    assert bool((pop[seg][:-1] >= pop[seg][1:]).all())

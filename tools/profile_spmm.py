@@ -20,7 +20,7 @@ ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--nodes", type=int)
 ap.add_argument("--edges", type=int)
 ap.add_argument("--width", type=int)
-ap.add_argument("--variant", default="plain", choices=["plain", "gcn_layer", "col_scale", "push", "chase", "sumsq"],
+ap.add_argument("--variant", default="plain", choices=["plain", "gcn_layer", "col_scale", "push", "chase", "sumsq", "hot_first"],
                 help="which launch of the hot kernel to run: plain fwd+bwd; the GCN-layer epilogue (weighted + bias + PReLU "
                      "+ z); the general mode (col_scale); the fused halo push / chase exchange with a local stand-in peer")
 a = ap.parse_args()
@@ -29,7 +29,9 @@ n, m, d = a.nodes or n, a.edges or m, a.width or d
 g = synth.rmat_shard(n, m, seed=0)
 gt = g.T
 x = torch.randn(n, d, device="cuda")
-if a.variant == "plain":
+if a.variant == "hot_first":
+    g, gt = g.reorder_edges_hot_first(), gt.reorder_edges_hot_first()
+if a.variant in ("plain", "hot_first"):
     for _ in range(a.iters):
         y = ops.gather_reduce(g, x)["y"]
         dx = ops.gather_reduce(gt, y)["y"]
