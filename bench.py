@@ -359,10 +359,10 @@ def native(args):
         else:
             row_cost = float(args.row_cost)
             br, bwd = build_bwd(row_cost)
-    if args.edge_order == "hot-first":
+    if args.edge_order in ("hot-first", "serpentine"):
         # plan-time re-ordering of every row's edges by column popularity (CSRGraph.reorder_edges_hot_first)
-        fwd = fwd.reorder_edges_hot_first()
-        bwd = bwd.reorder_edges_hot_first()
+        fwd = fwd.reorder_edges_hot_first(serpentine=args.edge_order == "serpentine")
+        bwd = bwd.reorder_edges_hot_first(serpentine=args.edge_order == "serpentine")
     for g in (fwd, bwd):
         g.plan
     torch.cuda.synchronize()
@@ -882,7 +882,7 @@ def main():
                          "a timed trial split (profile-guided)")
     ap.add_argument("--peer-debug", default=None, choices=["zero_mask", "local_peers"],
                     help="diagnostics only (results are NOT exchanged): isolate the cost of the peer stores")
-    ap.add_argument("--edge-order", default="column", choices=["column", "hot-first"],
+    ap.add_argument("--edge-order", default="column", choices=["column", "hot-first", "serpentine"],
                     help="order of the edges inside a CSR row: by column id (as a CSR build leaves them) or most popular "
                          "column first (homogeneous L2-hit / DRAM-miss batches)")
     ap.add_argument("--no-e2e", action="store_true")

@@ -188,20 +188,24 @@ class CSRGraph:
         g._plan = self._plan
         return g
 
-    def reorder_edges_hot_first(self, col_weight: Optional[torch.Tensor] = None) -> "CSRGraph":
+    def reorder_edges_hot_first(self, col_weight: Optional[torch.Tensor] = None, serpentine: bool = False) -> "CSRGraph":
         """Same operator with the edges of every row re-ordered by the popularity of their column (most gathered
         column first; ``col_weight`` defaults to the exact integer in-degree histogram of ``col``).  Pure index work,
         done once per graph on the device.  Why: the kernel gathers U rows per lane group at a time and a batch
         completes at the latency of its slowest row; popular columns are the ones resident in L2, so this order makes
         the batches homogeneous -- all-hit batches finish at L2 latency instead of waiting for one DRAM miss.  The
-        result differs from the column-sorted order only in the fp32 summation order (still deterministic)."""
+        result differs from the column-sorted order only in the fp32 summation order (still deterministic).
+        ``serpentine``: odd rows are ordered coldest-first, so that consecutive rows meet hot-to-hot and cold-to-cold
+        (rows are shorter than a few batches; a lane group walks them back to back)."""
         if self.nnz == 0:
             return self
         dev = self.device
         w = torch.bincount(self.col, minlength=self.n_cols) if col_weight is None else col_weight.to(torch.int64)
         rows = torch.repeat_interleave(torch.arange(self.n_rows, device=dev), self.degrees())
         top = int(w.max().item()) + 1
-        key = rows * top + (top - 1 - w[self.col.long()])
+        wc = w[self.col.long()]
+        key = rows * top + (torch.where((rows & 1) == 1, wc, top - 1 - wc) if serpentine else (top - 1 - wc))
+        del wc
         del rows
         perm = torch.argsort(key)
         del key
