@@ -45,6 +45,17 @@ class ChaseDesc(C.Structure):
     ]
 
 
+class TailDesc(C.Structure):
+    """Mirror of ggad_tail_desc_t."""
+    _fields_ = [
+        ("combined", _vp), ("ld_combined", C.c_int64), ("ego", _vp), ("ld_ego", C.c_int64), ("fc", _vp), ("weight", _vp),
+        ("labels", _vp), ("batch", C.c_int32), ("h", C.c_int32), ("rows", _vp), ("apre_src", _vp), ("apre_own", _vp),
+        ("scores", _vp), ("bce", _vp), ("cos", _vp), ("dist", _vp), ("norms", _vp), ("src", _vp), ("out", _vp),
+        ("grad_total", _vp), ("d_combined", _vp), ("ld_d_combined", C.c_int64), ("d_apre", _vp), ("d_ego", _vp),
+        ("d_scores", _vp), ("d_weight", _vp),
+    ]
+
+
 class ResidentCSR(C.Structure):
     """Mirror of ggad_resident_csr_t."""
     _fields_ = [
@@ -84,6 +95,8 @@ SIGNATURES = {
     "ggad_unique_sorted": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
     "ggad_block_remap": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp]),
     "ggad_block_col_weights": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    "ggad_minibatch_tail_fwd": (C.c_int, [C.POINTER(TailDesc), _vp]),
+    "ggad_minibatch_tail_bwd": (C.c_int, [C.POINTER(TailDesc), _vp]),
     "ggad_rmat_keys": (C.c_int, [_vp, _i64, _i64, _i32, _i32, C.c_uint64, _f, _f, _f, _i64, _i64, _vp, _vp]),
     "ggad_spmm_fwd_bwd_host": (C.c_int, [C.POINTER(ResidentCSR), C.POINTER(ResidentCSR), _vp, _vp, _vp, _vp, _i32,
                                          _vp, _vp, _vp, _vp, _vp]),

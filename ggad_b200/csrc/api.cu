@@ -82,6 +82,8 @@ int rmat_keys_impl(uint64_t*, int64_t, int64_t, int32_t, int32_t, uint64_t, floa
 
 int halo_push_impl(const float*, int64_t, int64_t, int32_t, const uint32_t*, float* const*, int32_t, cudaStream_t);
 int halo_chase_impl(const ggad_chase_desc_t*, cudaStream_t);
+int minibatch_tail_fwd_impl(const ggad_tail_desc_t*, cudaStream_t);
+int minibatch_tail_bwd_impl(const ggad_tail_desc_t*, cudaStream_t);
 int block_col_weights_impl(const int32_t*, int64_t, int32_t*, int64_t, float*, cudaStream_t);
 int csr_row_sum_f64_impl(const int64_t*, const float*, int64_t, double*, cudaStream_t);
 int csr_add_identity_rowptr_impl(const int64_t*, const int32_t*, int64_t, int64_t*, int64_t*, cudaStream_t);
@@ -300,6 +302,13 @@ GGAD_API int ggad_block_remap(const int32_t* cols, int64_t nnz, const int32_t* u
 GGAD_API int ggad_block_col_weights(const int32_t* block_col, int64_t nnz, int32_t* counts, int64_t n_nodes, float* val,
                                     ggad_stream_t stream) {
   return block_col_weights_impl(block_col, nnz, counts, n_nodes, val, (cudaStream_t)stream);
+}
+
+GGAD_API int ggad_minibatch_tail_fwd(const ggad_tail_desc_t* desc, ggad_stream_t stream) {
+  return minibatch_tail_fwd_impl(desc, (cudaStream_t)stream);
+}
+GGAD_API int ggad_minibatch_tail_bwd(const ggad_tail_desc_t* desc, ggad_stream_t stream) {
+  return minibatch_tail_bwd_impl(desc, (cudaStream_t)stream);
 }
 
 GGAD_API int ggad_rmat_keys(uint64_t* keys, int64_t n_edges, int64_t n_local, int32_t n_shards, int32_t shard, uint64_t seed, float a,

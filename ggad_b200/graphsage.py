@@ -41,6 +41,11 @@ def _device_of(features, fallback=None) -> torch.device:
 
 _table_cache = {}
 
+# GCN.loss: run everything after the two projections as the fused tail kernels (csrc/tail.cu) instead of ~100 small torch
+# kernels; GGAD_TORCH_TAIL=1 keeps the torch formulation (the two are parity-tested against each other)
+import os as _os
+FUSED_TAIL = not _os.environ.get("GGAD_TORCH_TAIL")
+
 
 def _feature_table(features) -> Optional[torch.Tensor]:
     """The frozen feature table as a 16-byte-row CUDA matrix, or None when ``features`` is a callable."""
@@ -483,6 +488,13 @@ class GCN(nn.Module):
         padding), the ego-mean mask (anything with ``.mm``) and the device label vector: every shape is static, which
         is what train.GraphedMiniBatchStep captures into a CUDA graph."""
         enc = self.enc
+        g_mean = getattr(mask, "_g", None) or getattr(mask, "g", None)
+        if FUSED_TAIL and g_mean is not None and enc.embed_dim <= 256 and enc.embed_dim % 4 == 0:
+            # projections on the GEMM kernel, everything after them in two fused launches (ops.minibatch_tail)
+            combined = ops.linear(neigh_feats, enc.weight, relu=True)            # [B,h]  (:412)
+            emb_u = ops.linear(neigh_feats_expand, enc.weight, relu=True)        # [|U|,h] (:419)
+            total, cls, margin, rec = ops.minibatch_tail(combined, emb_u, enc.fc.weight, self.weight, lab, g_mean)
+            return total, cls, margin, rec
         is_ab = lab == 1
         m1 = is_ab.to(torch.float32)
         m0 = (lab == 0).to(torch.float32)

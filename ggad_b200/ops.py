@@ -213,6 +213,66 @@ def linear(x: torch.Tensor, w: torch.Tensor, relu: bool = False) -> torch.Tensor
     return y.reshape(*lead, w.shape[0])
 
 
+class _MinibatchTail(torch.autograd.Function):
+    """The dense tail of a mini-batch GGAD training batch as two fused launches (ggad_minibatch_tail_fwd / _bwd,
+    csrc/tail.cu; formulas in include/ggad_b200.h).  Inputs: combined [B,h] (post-ReLU projection), emb_u [|U|,h]
+    (post-ReLU hop-1 frontier embeddings), the ego-mean operator (CSRGraph [B,|U|], row_scale 1/rdeg), fc [h,h],
+    weight [1,h], labels [B] in {0,1}.  Returns the four loss tensors of src/graphsage.py:244-258; only ``total``
+    is differentiable."""
+
+    @staticmethod
+    def forward(ctx, combined, emb_u, fc, weight, lab, g_mean):
+        dev, (b, h) = combined.device, combined.shape
+        ego = gather_reduce(g_mean, emb_u.contiguous())["y"]                     # [B,h] ego-neighbor mean (:421)
+        comb = _rowmajor(combined)
+        f32 = dict(dtype=torch.float32, device=dev)
+        st = dict(rows=torch.empty(b, h, **f32), apre_src=torch.empty(b, h, **f32), apre_own=torch.empty(b, h, **f32),
+                  scores=torch.empty(b, **f32), bce=torch.empty(b, **f32), cos=torch.empty(b, **f32),
+                  dist=torch.empty(b, **f32), norms=torch.empty(2 * b, **f32),
+                  src=torch.empty(b, dtype=torch.int32, device=dev), out=torch.empty(8, **f32))
+        d = _lib.TailDesc()
+        d.combined, d.ld_combined, d.ego, d.ld_ego = ptr(comb), comb.stride(0), ptr(ego), ego.stride(0)
+        fcc, wc, labc = fc.contiguous(), weight.reshape(-1).contiguous(), lab.to(torch.int64).contiguous()
+        d.fc, d.weight, d.labels, d.batch, d.h = ptr(fcc), ptr(wc), ptr(labc), b, h
+        for k, v in st.items():
+            setattr(d, k, ptr(v))
+        with torch.cuda.device(dev):
+            check(lib().ggad_minibatch_tail_fwd(d, stream_ptr(dev)))
+        ctx.g_mean, ctx.st = g_mean, st
+        ctx.save_for_backward(comb, ego, fcc, wc, labc, emb_u)
+        out = st["out"]
+        total, cls, margin, rec = out[0:1].clone(), out[1].clone(), out[2:3].clone(), out[3].clone()
+        ctx.mark_non_differentiable(cls, margin, rec)
+        return total, cls, margin, rec
+
+    @staticmethod
+    def backward(ctx, g_total, *_unused):
+        comb, ego, fcc, wc, labc, emb_u = ctx.saved_tensors
+        dev, (b, h), st = comb.device, comb.shape, ctx.st
+        f32 = dict(dtype=torch.float32, device=dev)
+        d_comb, d_apre, d_ego = torch.empty(b, h, **f32), torch.empty(b, h, **f32), torch.empty(b, h, **f32)
+        d_scores, d_w = torch.empty(b, **f32), torch.empty(h, **f32)
+        d = _lib.TailDesc()
+        d.combined, d.ld_combined, d.ego, d.ld_ego = ptr(comb), comb.stride(0), ptr(ego), ego.stride(0)
+        d.fc, d.weight, d.labels, d.batch, d.h = ptr(fcc), ptr(wc), ptr(labc), b, h
+        for k, v in st.items():
+            setattr(d, k, ptr(v))
+        gt = g_total.reshape(-1).to(torch.float32).contiguous()
+        d.grad_total, d.d_combined, d.ld_d_combined = ptr(gt), ptr(d_comb), h
+        d.d_apre, d.d_ego, d.d_scores, d.d_weight = ptr(d_apre), ptr(d_ego), ptr(d_scores), ptr(d_w)
+        with torch.cuda.device(dev):
+            check(lib().ggad_minibatch_tail_bwd(d, stream_ptr(dev)))
+        d_fc = dense_matmul(d_apre, ego, trans_a=True) if ctx.needs_input_grad[2] else None       # d fc = d_apre^T ego
+        d_emb = gather_reduce(ctx.g_mean.T, d_ego)["y"] if ctx.needs_input_grad[1] else None       # through the mean operator
+        return (d_comb if ctx.needs_input_grad[0] else None), d_emb, d_fc, \
+            (d_w.reshape(1, -1) if ctx.needs_input_grad[3] else None), None, None
+
+
+def minibatch_tail(combined, emb_u, fc, weight, lab, g_mean: CSRGraph):
+    """(total [1], cls, margin [1], rec) of a mini-batch GGAD batch from the projected aggregates (see _MinibatchTail)."""
+    return _MinibatchTail.apply(combined, emb_u, fc, weight, lab, g_mean)
+
+
 def halo_push(y: torch.Tensor, y_peers, peer_need: Optional[torch.Tensor] = None) -> None:
     """Store the rows of ``y`` [n, d] (a rank's own block of a replicated matrix) into the peers' replicas over
     NVLink: row r goes to ``y_peers[p]`` (peer-mapped device addresses of the same block) iff bit p of

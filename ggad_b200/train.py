@@ -136,7 +136,10 @@ class GraphedMiniBatchStep:
         self.g, self.gt = g, gt
         outer = self
 
-        class _Mask:                       # what loss_from_aggregates calls .mm on
+        class _Mask:                       # what loss_from_aggregates calls .mm on / takes the operator from
+            def __init__(self):
+                self.g = g
+
             def mm(self, x):
                 from . import ops
                 return ops.spmm(g, x.contiguous())

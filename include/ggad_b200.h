@@ -212,6 +212,44 @@ GGAD_API int ggad_dense_matmul(int32_t trans_a, int32_t trans_b, int64_t m, int6
 GGAD_API int ggad_plan_build_padded(const int64_t* rowptr, int64_t n_rows, int64_t nnz, int64_t n_tiles, int32_t* tile_row,
                                     int64_t* tile_edge, ggad_stream_t stream);
 
+/* ---- K6 (mini-batch): the dense tail of a GGAD training batch, fused -------------------------------------
+ * From combined [B,h] = ReLU(W agg^T)^T (src/graphsage.py:412), ego [B,h] = mask_row . emb_U (:421), fc [h,h] (:430),
+ * weight [h] (:174) and labels [B] in {0,1}: outlier generation ReLU(fc ego), the label-0-first column permutation of
+ * combined_all (:450), scores + BCE-with-logits against the un-permuted labels (:246), the cosine local affinity of
+ * column p against ego row p and its margin (:234-240), the reconstruction term (:197-198) and
+ * total = cls + margin + 0.1 rec (:258) -- one CTA per batch position + a one-CTA reduction.  out[0..3] = total, cls,
+ * margin, rec.  ggad_minibatch_tail_bwd is the hand-derived backward for d total (grad_total: device float): it fills
+ * d_combined [B,ld], d_apre [B,h] (gradient w.r.t. fc ego before the ReLU; d fc = d_apre^T ego is one
+ * ggad_dense_matmul), d_ego [B,h] (to be pushed through the transposed ego-mean operator), d_scores [B], d_weight [h].
+ * All buffers are caller-owned device memory; the forward outputs (rows, apre_src, apre_own, scores, bce, cos, dist, norms, src, out) are the saved
+ * state the backward reads.  Deterministic (single writers or two commutative atomic adds per element). */
+typedef struct ggad_tail_desc {
+  const float* combined; int64_t ld_combined;
+  const float* ego; int64_t ld_ego;
+  const float* fc;        /* [h,h] row-major (nn.Linear weight) */
+  const float* weight;    /* [h] */
+  const int64_t* labels;  /* [B] */
+  int32_t batch, h;
+  float* rows;            /* [B,h]  R = combined_all^T */
+  float* apre_src;        /* [B,h]  fc ego[src[p]] for positions whose source row has label 1 */
+  float* apre_own;        /* [B,h]  fc ego[p] for rows with label 1 */
+  float* scores;          /* [B] */
+  float* bce;             /* [B] */
+  float* cos;             /* [B] */
+  float* dist;            /* [B] */
+  float* norms;           /* [2B] */
+  int32_t* src;           /* [B] source row of position p */
+  float* out;             /* [8] */
+  const float* grad_total; /* backward only: d loss / d total (device scalar) */
+  float* d_combined; int64_t ld_d_combined;
+  float* d_apre;          /* [B,h] */
+  float* d_ego;           /* [B,h] */
+  float* d_scores;        /* [B] */
+  float* d_weight;        /* [h] */
+} ggad_tail_desc_t;
+GGAD_API int ggad_minibatch_tail_fwd(const ggad_tail_desc_t* desc, ggad_stream_t stream);
+GGAD_API int ggad_minibatch_tail_bwd(const ggad_tail_desc_t* desc, ggad_stream_t stream);
+
 /* ---- K4: backward helper of the local-affinity cosine ---------------------------
  * de_k = ( g_k - e^_k <e^_k, g_k> ) * inv_norm_k   with e^_k = e_k * inv_norm_k, in place on g.
  * (autograd of run.py:177-180.) */

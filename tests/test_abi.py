@@ -67,6 +67,7 @@ def test_struct_layout_matches_header():
     assert fields("ggad_gather_desc") == [f[0] for f in _lib.GatherDesc._fields_]
     assert fields("ggad_resident_csr") == [f[0] for f in _lib.ResidentCSR._fields_]
     assert fields("ggad_chase_desc") == [f[0] for f in _lib.ChaseDesc._fields_]
+    assert fields("ggad_tail_desc") == [f[0] for f in _lib.TailDesc._fields_]
 
 
 def test_sass_is_blackwell_native(libpath):

@@ -109,6 +109,21 @@ def test_minibatch_model_matches_reference(name):
     for t, u in zip(model.loss(nodes, labels), (total, cls, margin, rec)):
         assert torch.equal(t, u), "prefetched blocks changed the result"
     agg.prefetcher = None
+    # the fused tail kernels (csrc/tail.cu, what model.loss ran above) against the torch formulation of the same tail
+    fused_grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.requires_grad}
+    gs.FUSED_TAIL = False
+    try:
+        model.zero_grad()
+        out_t = model.loss(nodes, labels)
+        out_t[0].backward()
+    finally:
+        gs.FUSED_TAIL = True
+    for t, u, k in zip(out_t, (total, cls, margin, rec), ("total", "cls", "margin", "rec")):
+        assert_close(t, u, rtol=1e-5, atol=1e-6, what=f"fused tail vs torch tail: {k}")
+        assert t.shape == u.shape
+    for k, p in model.named_parameters():
+        if p.requires_grad:
+            assert_close(fused_grads[k], p.grad, rtol=2e-4, atol=2e-6, what=f"fused tail vs torch tail: grad {k}")
     with torch.no_grad():
         assert_close(model.to_prob(nodes, None), o["prob"], what="to_prob")
         to_feats, to_feats_neigh, mask = agg.forward(nodes, [adj[v] for v in nodes], adj, True)
