@@ -766,7 +766,8 @@ def _e2e_leg(args, world, rank, dev, fwd, bwd, fr, br, value, rep=None, need_y=N
     sec = float(t.item())
     res = {"value": args.edges * world / sec, "unit": "edges/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": sec * 1e3, "steps": steps, "api": api,
-           "host_link_GBs_achieved": round((h2d + d2h) / sec / 1e9, 1)}
+           "host_link_GBs_achieved": round((h2d + d2h) / sec / 1e9, 1),                 # per rank, both directions
+           "host_link_GBs_aggregate": round(world * (h2d + d2h) / sec / 1e9, 1)}        # the box's host memory serves all ranks
     if world == 1:
         res["host_link"] = link
     return res
