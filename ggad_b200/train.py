@@ -95,8 +95,8 @@ class GraphedMiniBatchStep:
     cost 3.3 ms of host time when issued eagerly.  Capacities grow by doubling (one re-capture).  Results equal
     ``model.loss(...).backward(); opt.step()`` (tested)."""
 
-    def __init__(self, model, lr: float = 1e-3, weight_decay: float = 0.0, batch_rows: int = 200, u_cap: int = 1 << 15,
-                 e_cap: int = 1 << 17, warmup: int = 2, group=None):
+    def __init__(self, model, lr: float = 1e-3, weight_decay: float = 0.0, batch_rows: int = 200, u_cap: int = 1 << 16,
+                 e_cap: int = 1 << 18, warmup: int = 2, group=None):
         import torch.distributed as dist
         from . import graphsage as gs
         self.model, self.gs = model, gs
