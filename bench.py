@@ -799,14 +799,14 @@ def reference(args):
 
 def minibatch_workload(args):
     """--workload C4mb: one step = one training batch of program B (150 + 50 nodes: device frontier, two gathers,
-    dense tail, backward, Adam; src/model_handler.py:330-364) on the DGraph-shaped synthetic graph; N ranks = data
-    parallel replicas with their own seed batches.  Re-emits tools/bench_minibatch.py's result in the bench contract."""
+    fused dense tail, backward, Adam replayed as a CUDA graph -- train.GraphedMiniBatchStep; src/model_handler.py:330-364)
+    on the DGraph-shaped synthetic graph; N ranks = data parallel replicas with their own seed batches.  Re-emits tools/bench_minibatch.py's result in the bench contract."""
     import io
     import contextlib
     import runpy
     rank = int(os.environ.get("RANK", "0"))
     argv = ["bench_minibatch.py", "--nodes", str(args.nodes), "--edges", str(args.edges), "--d", str(args.width),
-            "--iters", str(max(10, args.steps)), "--warm", str(max(3, args.warmup))]
+            "--iters", str(max(10, args.steps)), "--warm", str(max(3, args.warmup)), "--graphed", "--no-prefetch"]
     argv += ["--cpu-nodes", "0"] if (args.no_cpu or args.impl != "reference") else []
     old = sys.argv
     sys.argv = argv
