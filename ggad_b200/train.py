@@ -106,10 +106,13 @@ class GraphedMiniBatchStep:
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.dist, self.group = dist, group
-        # with one rank Adam is part of the graph; data parallel: fwd + bwd are graphed, the gradient all-reduce and a
-        # fused Adam step follow eagerly
-        self.opt = torch.optim.Adam(self.params, lr=lr, weight_decay=weight_decay, capturable=True, fused=self.world > 1 or None)
+        # with one rank Adam is part of the graph; data parallel: see self.flat below
+        self.opt = torch.optim.Adam(self.params, lr=lr, weight_decay=weight_decay, capturable=True)
         self.graph = None
+        self.graph_b = None
+        # data parallel: graph A = forward + backward + "flatten the gradients into self.flat"; eager NCCL all-reduce of
+        # that one buffer; graph B = average + Adam reading the gradients through views of it -- three launches per batch
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=self.dev) if self.world > 1 else None
         self._alloc(u_cap, e_cap)
 
     def _alloc(self, u_cap, e_cap):
@@ -144,7 +147,7 @@ class GraphedMiniBatchStep:
                 from . import ops
                 return ops.spmm(g, x.contiguous())
         self.mask = _Mask()
-        self.graph, self.out = None, None
+        self.graph, self.graph_b, self.out = None, None, None
 
     def _tail(self):
         for p in self.params:
@@ -154,7 +157,28 @@ class GraphedMiniBatchStep:
         out[0].backward()
         if self.world == 1:
             self.opt.step()
+        else:
+            o = 0
+            for p in self.params:
+                n = p.numel()
+                if p.grad is None:
+                    self.flat[o:o + n].zero_()
+                else:
+                    self.flat[o:o + n].copy_(p.grad.reshape(-1))
+                o += n
         return tuple(t.detach() for t in out)
+
+    def _views(self):
+        """Point every parameter's .grad at its slice of the flat buffer (what graph B's Adam reads)."""
+        o = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[o:o + n].view_as(p)
+            o += n
+
+    def _apply(self):
+        self.flat.div_(self.world)
+        self.opt.step()
 
     def _capture(self):
         dev = self.dev
@@ -168,7 +192,8 @@ class GraphedMiniBatchStep:
             for _ in range(max(1, self.warmup)):          # warms the allocator, creates the Adam state tensors
                 self._tail()
                 if self.world > 1:
-                    self.opt.step()
+                    self._views()
+                    self._apply()
             with torch.no_grad():
                 for p, s_ in zip(self.params, state):
                     p.copy_(s_)
@@ -184,6 +209,11 @@ class GraphedMiniBatchStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = self._tail()
+        if self.world > 1:
+            self._views()
+            self.graph_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_b):
+                self._apply()
 
     def _load(self, nodes, labels):
         """Eager, per batch: hop blocks (or the prefetched ones), the two gathers from the feature table into the static
@@ -227,14 +257,8 @@ class GraphedMiniBatchStep:
             self._capture()
         self.graph.replay()
         if self.world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in self.params])
-            self.dist.all_reduce(flat, group=self.group)
-            flat /= self.world
-            o = 0
-            for p in self.params:
-                p.grad.copy_(flat[o:o + p.numel()].reshape(p.shape))
-                o += p.numel()
-            self.opt.step()
+            self.dist.all_reduce(self.flat, group=self.group)
+            self.graph_b.replay()
         return self.out
 
 

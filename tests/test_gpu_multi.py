@@ -217,6 +217,18 @@ def _dp_worker(rank, world, port, q):
             if a.requires_grad and not torch.allclose(a, b, rtol=1e-4, atol=1e-6):
                 ok = False
                 msg += f"{k}: max diff {float((a - b).abs().max()):.3e} "
+    # the CUDA-graph form of the same step (graph A: forward + backward + flatten, NCCL all-reduce, graph B: average +
+    # Adam) follows the same trajectory
+    from ggad_b200.train import GraphedMiniBatchStep
+    m2, _ = make()
+    stepper = GraphedMiniBatchStep(m2, lr=1e-2, batch_rows=B, u_cap=4096, e_cap=16384)
+    for it in range(3):
+        stepper.step(batches[it][rank], labels)
+    torch.cuda.synchronize()
+    for (k, a), (_, b) in zip(m2.named_parameters(), m.named_parameters()):
+        if a.requires_grad and not torch.allclose(a, b, rtol=2e-4, atol=2e-6):
+            ok = False
+            msg += f"graphed {k}: max diff {float((a - b).abs().max()):.3e} "
     w = m.weight.detach().clone()
     lo, hi = w.clone(), w.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN)
