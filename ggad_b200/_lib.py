@@ -31,7 +31,7 @@ class GatherDesc(C.Structure):
         ("dot_out", _vp),
         ("tile_row", _vp), ("tile_edge", _vp), ("n_tiles", C.c_int64), ("ws", _vp),
         ("y_peer", _vp * 7), ("n_peer", C.c_int32), ("tile_epoch", C.c_int32), ("y_multicast", _vp), ("peer_need", _vp),
-        ("tile_done", _vp), ("mc_min_peers", C.c_int32), ("reserved2", C.c_int32),
+        ("tile_done", _vp), ("mc_min_peers", C.c_int32), ("n_x_rows", C.c_int32),
     ]
 
 

@@ -58,7 +58,11 @@ struct GatherArgs {
   int32_t* tile_done;   // chase mode: tile k publishes tile_done[k] = tile_epoch instead of pushing its rows
   int32_t tile_epoch;
   int32_t mc_min;       // hybrid exchange: rows needed by >= mc_min peers take the multicast address (0: y_mc takes all)
+  int32_t n_x_rows;     // rows of x (0: not given); the TMA row-staging variant bounds its tensor map with it
 };
+
+// gather_tma.cu: rows staged through shared memory by TMA (A/B variant, GGAD_TMA_ROWS); -1 = not selected / not applicable
+int try_launch_tma_rows(const GatherArgs& a, cudaStream_t st);
 
 constexpr int kThreads = 256;
 constexpr int kTile = GGAD_TILE_ITEMS;
@@ -830,6 +834,12 @@ int launch_variant(const GatherArgs& a, cudaStream_t st, int sm_count) {
       return epi == 1 ? launch_mode<G, CH, 1, true>(a, st) : launch_mode<G, CH, 0, true>(a, st);
     }
     if (epi == 2) return launch_mode<G, CH, 2, false>(a, st);
+    if constexpr (G == 16 && CH == 1) {
+      if (epi == 0) {
+        const int r = try_launch_tma_rows(a, st);
+        if (r >= 0) return r;
+      }
+    }
     return epi == 1 ? launch_mode<G, CH, 1, false>(a, st) : launch_mode<G, CH, 0, false>(a, st);
   }
   GGAD_REQUIRE(!peer, GGAD_ERR_UNSUPPORTED, "gather_reduce: peer / multicast stores need the merge-path plan");

@@ -92,6 +92,7 @@ int gather_reduce_impl(const ggad_gather_desc_t* d, cudaStream_t st) {
   a.tile_done = d->tile_done;
   a.tile_epoch = d->tile_epoch;
   a.mc_min = d->mc_min_peers;
+  a.n_x_rows = d->n_x_rows;
   GGAD_REQUIRE(!a.tile_done || (d->tile_row && d->y && !a.y_mc), GGAD_ERR_INVALID,
                "gather_reduce: tile_done (chase mode) needs the merge-path plan and y, and excludes y_multicast");
   GGAD_REQUIRE((d->n_peer == 0 && !a.y_mc) || d->y, GGAD_ERR_INVALID, "gather_reduce: the fused exchange needs the local y");

@@ -72,6 +72,7 @@ def gather_reduce(g: CSRGraph, x: torch.Tensor, *, xmap: Optional[torch.Tensor] 
     desc.rowptr, desc.col, desc.val = ptr(g.rowptr), ptr(g.col), ptr(g.val)
     desc.n_rows, desc.nnz = g.n_rows, g.nnz
     desc.x, desc.ldx = ptr(x), x.stride(0)
+    desc.n_x_rows = min(int(x.shape[0]), 2**31 - 1)
     desc.xmap, desc.col_scale, desc.row_scale = ptr(xmap), ptr(col_scale), ptr(row_scale)
     desc.d, desc.relu = d, int(bool(relu))
     desc.bias, desc.prelu_slope = ptr(bias), ptr(prelu_slope)

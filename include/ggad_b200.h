@@ -140,7 +140,9 @@ typedef struct ggad_gather_desc {
    * stored once through the multicast address (it lands in every rank's replica) instead of once per peer that
    * needs it; 0 = off (y_multicast alone then means: every row through the multicast address). */
   int32_t mc_min_peers;
-  int32_t reserved2;
+  /* number of rows of x, or 0 when the caller does not state it.  Only the TMA row-staging variant of the kernel
+   * (environment GGAD_TMA_ROWS, an A/B knob) needs it, to bound its tensor map; it is skipped when this is 0. */
+  int32_t n_x_rows;
 } ggad_gather_desc_t;
 
 GGAD_API int ggad_gather_reduce(const ggad_gather_desc_t* desc, ggad_stream_t stream);

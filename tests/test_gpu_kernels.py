@@ -650,3 +650,35 @@ def test_hot_first_edge_order_is_the_same_operator():
     r = 4000
     seg = h.col[int(h.rowptr[r]):int(h.rowptr[r + 1])].long()
     assert bool((pop[seg][:-1] >= pop[seg][1:]).all())
+
+
+@pytest.mark.parametrize("kind,stages", [(1, 4), (1, 2), (1, 5), (2, 4), (2, 3), (3, 1), (3, 2), (3, 3)])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_tma_row_staging_variant_is_bit_identical(kind, stages, weighted, monkeypatch):
+    """The A/B variant that stages the neighbour rows through shared memory with TMA (GGAD_TMA_ROWS=1: tile::gather4
+    tensor copies, 2: one bulk copy per row, 3: gather4 with the two lane groups of a warp in lock step) keeps the tile split and the summation order of gather_tiled_kernel, so its
+    result must equal the shipped kernel's bit for bit, and the oracle's within the usual tolerance.  Hub rows, empty
+    rows, ragged group ends (batches of fewer than four edges) are all in the graph."""
+    _, _, graph, ops, _ = _mods()
+    n, nc = 30000, 21000
+    rowptr, col, val = make_csr(n, nc, 14.0, seed=21, hub=9000)
+    g = graph.CSRGraph.from_arrays(rowptr, col, val if weighted else None, n, nc, use_plan=True)
+    x = torch.randn(nc + 3, 64)
+    xd = x.cuda()
+    monkeypatch.delenv("GGAD_TMA_ROWS", raising=False)
+    y0 = ops.gather_reduce(g, xd)["y"]
+    monkeypatch.setenv("GGAD_TMA_ROWS", str(kind))
+    monkeypatch.setenv("GGAD_TMA_STAGES", str(stages))
+    names = []
+    try:
+        with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+            y1 = ops.gather_reduce(g, xd)["y"]
+            torch.cuda.synchronize()
+        names = [e.name for e in prof.events()]
+    except RuntimeError:                      # no CUPTI on this box: run without the kernel-name check
+        y1 = ops.gather_reduce(g, xd)["y"]
+    assert torch.equal(y0, y1)
+    if any("gather" in nm for nm in names):
+        assert any("gather_tma_kernel" in nm for nm in names), names
+    ref = oracle.spmm_csr(rowptr, col, val if weighted else np.ones_like(val), x[:nc])
+    assert_close(y1, ref, rtol=RTOL, atol=3e-4, what="TMA-staged rows")

@@ -32,12 +32,28 @@ def timeit(fn, iters=10, warm=3):
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="S64")
 ap.add_argument("--no-chase", action="store_true", help="skip the chase-mode lines (variant libraries that do not flag tiles)")
+ap.add_argument("--tma-ab", action="store_true",
+                help="only the plain launches, register-direct gathers vs rows staged by TMA (GGAD_TMA_ROWS / GGAD_TMA_STAGES)")
 a = ap.parse_args()
 n, m, d = WORKLOADS[a.workload]
 g = synth.rmat_shard(n, m, seed=0)
 gw = CSRGraph(g.rowptr, g.col, torch.rand(g.nnz, device="cuda"), n, n)
 gw._plan = g.plan
 x = torch.randn(n, d, device="cuda")
+if a.tma_ab:
+    print(f"workload {a.workload}: n={n} nnz={m} d={d}  (median of 10, CUDA events)")
+    y_ref = ops.gather_reduce(g, x)["y"].clone()
+    for kind, stages, promo in [(0, 0, 3), (1, 1, 3), (1, 2, 3), (1, 2, 0), (1, 3, 3), (1, 4, 3), (1, 4, 0), (1, 5, 3), (2, 1, 3), (2, 2, 3),
+                                (2, 4, 3), (2, 5, 3), (3, 1, 3), (3, 2, 3), (3, 3, 3)]:
+        os.environ["GGAD_TMA_ROWS"], os.environ["GGAD_TMA_STAGES"] = str(kind), str(stages)
+        os.environ["GGAD_TMA_L2_PROMOTION"] = str(promo)
+        same = bool(torch.equal(ops.gather_reduce(g, x)["y"], y_ref))
+        tu = timeit(lambda: ops.gather_reduce(g, x))
+        tw = timeit(lambda: ops.gather_reduce(gw, x))
+        what = {0: "register-direct ld.global.nc (shipped)", 1: f"TMA tile::gather4, {stages} stages" + ("" if promo == 3 else ", no L2 promotion"), 2: f"cp.async.bulk per row, {stages} stages",
+                3: f"gather4, warp-converged, {stages} x 8-row stages"}[kind]
+        print(f"  {what:42s} unweighted {tu:7.3f} ms {m / tu / 1e6:7.2f} G edges/s   weighted {tw:7.3f} ms {m / tw / 1e6:7.2f} G edges/s   bit-identical {same}")
+    sys.exit(0)
 bias = torch.randn(d, device="cuda")
 slope = torch.tensor([0.25], device="cuda")
 cs = torch.rand(n, device="cuda") + 0.5

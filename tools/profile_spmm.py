@@ -31,7 +31,7 @@ gt = g.T
 x = torch.randn(n, d, device="cuda")
 if a.variant == "hot_first":
     g, gt = g.reorder_edges_hot_first(), gt.reorder_edges_hot_first()
-if a.variant in ("plain", "hot_first"):
+if a.variant in ("plain", "hot_first"):          # GGAD_TMA_ROWS / GGAD_TMA_STAGES in the environment select the TMA-staged rows
     for _ in range(a.iters):
         y = ops.gather_reduce(g, x)["y"]
         dx = ops.gather_reduce(gt, y)["y"]
