@@ -670,6 +670,18 @@ def _e2e_leg(args, world, rank, dev, fwd, bwd, fr, br, value, rep=None, need_y=N
                 dst.copy_(src, non_blocking=True)
             torch.cuda.synchronize()
             link[tag + "_GBs_alone"] = round(3 * src.numel() * 4 / (time.perf_counter() - t0) / 1e9, 1)
+        # ... and both directions at once on two streams: the ceiling of a step that overlaps its copies perfectly
+        s_in, s_out = slots[0]["stream"], torch.cuda.Stream(device=dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            with torch.cuda.stream(s_in):
+                slots[0]["bufs"][0].copy_(x_host, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                slots[0]["dx"].copy_(slots[0]["bufs"][2], non_blocking=True)
+        torch.cuda.synchronize()
+        both = 3 * (x_host.numel() + slots[0]["dx"].numel()) * 4 / (time.perf_counter() - t0) / 1e9
+        link["both_GBs_concurrent"] = round(both, 1)
         for i in range(n_slots):                # warm-up
             enqueue(i)
         torch.cuda.synchronize()
