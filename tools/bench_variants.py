@@ -43,16 +43,23 @@ x = torch.randn(n, d, device="cuda")
 if a.tma_ab:
     print(f"workload {a.workload}: n={n} nnz={m} d={d}  (median of 10, CUDA events)")
     y_ref = ops.gather_reduce(g, x)["y"].clone()
-    for kind, stages, promo in [(0, 0, 3), (1, 1, 3), (1, 2, 3), (1, 2, 0), (1, 3, 3), (1, 4, 3), (1, 4, 0), (1, 5, 3), (2, 1, 3), (2, 2, 3),
-                                (2, 4, 3), (2, 5, 3), (3, 1, 3), (3, 2, 3), (3, 3, 3)]:
+    cfgs = [(0, 0, 3, 0, 0), (1, 2, 3, 0, 0), (2, 2, 3, 0, 0), (3, 1, 3, 0, 0), (3, 2, 3, 0, 0)]
+    # kind 4: nt warps of every CTA on the TMA path, the rest register-direct; (kind, stages, promo, nt, weight/16)
+    cfgs += [(4, 1, 3, 0, 16), (4, 2, 3, 1, 10), (4, 2, 3, 2, 10), (4, 2, 3, 2, 7), (4, 2, 3, 2, 13), (4, 1, 3, 2, 10), (4, 4, 3, 1, 10),
+             (4, 2, 3, 3, 10), (4, 2, 3, 4, 10), (4, 3, 3, 2, 10)]
+    for kind, stages, promo, nt, wq in cfgs:
         os.environ["GGAD_TMA_ROWS"], os.environ["GGAD_TMA_STAGES"] = str(kind), str(stages)
         os.environ["GGAD_TMA_L2_PROMOTION"] = str(promo)
-        same = bool(torch.equal(ops.gather_reduce(g, x)["y"], y_ref))
+        os.environ["GGAD_TMA_WARPS"], os.environ["GGAD_TMA_WEIGHT"] = str(nt), str(wq)
+        y = ops.gather_reduce(g, x)["y"]
+        same = "bit-identical" if torch.equal(y, y_ref) else f"max |diff| {float((y - y_ref).abs().max()):.2e}"
         tu = timeit(lambda: ops.gather_reduce(g, x))
         tw = timeit(lambda: ops.gather_reduce(gw, x))
-        what = {0: "register-direct ld.global.nc (shipped)", 1: f"TMA tile::gather4, {stages} stages" + ("" if promo == 3 else ", no L2 promotion"), 2: f"cp.async.bulk per row, {stages} stages",
-                3: f"gather4, warp-converged, {stages} x 8-row stages"}[kind]
-        print(f"  {what:42s} unweighted {tu:7.3f} ms {m / tu / 1e6:7.2f} G edges/s   weighted {tw:7.3f} ms {m / tw / 1e6:7.2f} G edges/s   bit-identical {same}")
+        what = {0: "register-direct ld.global.nc (shipped)", 1: f"TMA tile::gather4, {stages} stages" + ("" if promo == 3 else ", no L2 promotion"),
+                2: f"cp.async.bulk per row, {stages} stages",
+                3: f"gather4, warp-converged, {stages} x 8-row stages",
+                4: f"mixed: {nt} TMA warps/CTA x {stages} stages, weight {wq}/16"}[kind]
+        print(f"  {what:48s} unweighted {tu:7.3f} ms {m / tu / 1e6:7.2f} G edges/s   weighted {tw:7.3f} ms {m / tw / 1e6:7.2f} G edges/s   {same}")
     sys.exit(0)
 bias = torch.randn(d, device="cuda")
 slope = torch.tensor([0.25], device="cuda")
