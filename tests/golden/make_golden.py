@@ -10,6 +10,10 @@ on the GPU box):   python tests/golden/make_golden.py
   here on the dense tensors the reference would hold, line for line in meaning.
 * Program B: ``/root/reference/src/graphsage.py`` is imported with a stub for
   its unused ``torch_geometric`` import (src/graphsage.py:8).
+* Data entry: ``/root/reference/utils.py`` is imported with stubs for ``dgl`` and
+  ``matplotlib`` (used only by functions outside the path) and its ``load_mat``,
+  ``preprocess_features`` and ``normalize_adj`` are run on synthetic ``.mat`` files
+  (``data_*`` cases).
 
 Each .npz stores inputs, the reference state_dict (``p/<key>``), outputs
 (``o/<name>``) and parameter gradients (``g/<key>``).
@@ -285,8 +289,74 @@ def sage_case(ref_sage, name, n, d, h, bsz, seed, gcn):
     print("wrote", name, "loss", float(loss))
 
 
+def _load_ref_utils():
+    """utils.py itself, with empty stand-ins for the plotting / dgl imports it does not need for load_mat."""
+    for name in ("dgl", "matplotlib", "matplotlib.pyplot", "matplotlib.mlab", "matplotlib.backends",
+                 "matplotlib.backends.backend_pdf", "seaborn"):
+        try:
+            __import__(name)
+        except Exception:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+    sys.modules["matplotlib.backends.backend_pdf"].__dict__.setdefault("PdfPages", object)
+    sys.modules["matplotlib"].__dict__.setdefault("use", lambda *a, **k: None)          # utils.py:179-181 run at import
+    sys.modules["matplotlib.pyplot"].__dict__.setdefault("rcParams", {})
+    spec = importlib.util.spec_from_file_location("ref_utils", os.path.join(REF, "utils.py"))
+    ref_utils = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_utils)
+    return ref_utils
+
+
+def data_case(ref_utils, name, dataset, n, d, seed, alt_keys, with_kinds):
+    """A synthetic .mat in the published layout -> the reference's load_mat / preprocess_features / normalize_adj."""
+    import contextlib
+    import io
+    import tempfile
+
+    import scipy.io as sio
+    rng = np.random.default_rng(seed)
+    m = sp.random(n, n, density=5.0 / n, random_state=rng, data_rvs=lambda k: np.ones(k))
+    network = sp.csr_matrix(((m + m.T) > 0).astype(np.float64))
+    attrs = sp.random(n, d, density=0.3, random_state=rng, data_rvs=lambda k: rng.integers(1, 5, k).astype(np.float64)).tolil()
+    attrs[5, :] = 0                                       # a node without attributes: 1 / rowsum = inf -> 0
+    label = (rng.random(n) < 0.08).astype(np.int64).reshape(n, 1)
+    mat = {("gnd" if alt_keys else "Label"): label, ("X" if alt_keys else "Attributes"): sp.csc_matrix(attrs),
+           ("A" if alt_keys else "Network"): sp.csc_matrix(network)}
+    if with_kinds:
+        str_l = (label[:, 0] * (rng.random(n) < 0.5)).astype(np.int64).reshape(1, n)
+        mat["str_anomaly_label"] = str_l
+        mat["attr_anomaly_label"] = (label[:, 0].reshape(1, n) - str_l)
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "dataset"))
+        sio.savemat(os.path.join(tmp, "dataset", dataset + ".mat"), mat)
+        os.chdir(tmp)
+        try:
+            random.seed(seed)
+            with contextlib.redirect_stdout(io.StringIO()):
+                out = ref_utils.load_mat(dataset)
+        finally:
+            os.chdir(cwd)
+    adj, feat, ano, all_idx, tr, va, te, ano2, str_a, attr_a, normal, abnormal = out
+    dense_feat, (coords, values, shape) = ref_utils.preprocess_features(feat)
+    store = {"i/network": network.toarray(), "i/attrs": attrs.toarray(), "i/label": label, "i/seed": seed,
+             "i/alt_keys": int(alt_keys), "i/dataset": dataset,
+             "o/adj": adj.toarray(), "o/feat": feat.toarray(), "o/ano_labels": ano, "o/all_idx": all_idx, "o/idx_train": tr,
+             "o/idx_val": va, "o/idx_test": te, "o/normal_label_idx": normal, "o/abnormal_label_idx": abnormal,
+             "o/pre_dense": np.asarray(dense_feat), "o/pre_coords": coords, "o/pre_values": values, "o/pre_shape": np.asarray(shape),
+             "o/normalize_adj": ref_utils.normalize_adj(adj).toarray()}
+    if with_kinds:
+        store.update({"i/str": mat["str_anomaly_label"], "i/attr": mat["attr_anomaly_label"], "o/str": str_a, "o/attr": attr_a})
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **store)
+    print(f"{name}: n={n} train={len(tr)} normal={len(normal)} abnormal={len(abnormal)}")
+
+
 def main():
     ref_model, ref_sage = _load_ref()
+    ref_utils = _load_ref_utils()
+    data_case(ref_utils, "data_toy", "toy", 400, 12, 3, alt_keys=False, with_kinds=True)
+    data_case(ref_utils, "data_amazon_keys", "Amazon", 900, 9, 11, alt_keys=True, with_kinds=False)
     full_batch_case(ref_model, "fb_sym_binary", "sym_binary", 64, 12, 16, 0, 0.02, 0.01)
     full_batch_case(ref_model, "fb_asym_weighted", "asym_weighted", 48, 10, 16, 72, 0.0, 0.0)
     full_batch_case(ref_model, "fb_isolated", "isolated", 56, 25, 20, 0, 0.02, 0.01)

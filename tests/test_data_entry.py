@@ -1,0 +1,91 @@
+"""Host-side data entry (ggad_b200.data: load_mat, preprocess_features, normalize_adj) against goldens produced by the
+reference's own utils.py on synthetic .mat files (tests/golden/make_golden.py::data_case).  CPU only."""
+import random
+
+import numpy as np
+import pytest
+import scipy.io as sio
+import scipy.sparse as sp
+
+import oracle
+from helpers import golden_cases, load_case
+
+
+def _write_mat(c, root):
+    alt = bool(int(c["i/alt_keys"]))
+    mat = {("gnd" if alt else "Label"): c["i/label"], ("X" if alt else "Attributes"): sp.csc_matrix(c["i/attrs"]),
+           ("A" if alt else "Network"): sp.csc_matrix(c["i/network"])}
+    if "i/str" in c:
+        mat["str_anomaly_label"], mat["attr_anomaly_label"] = c["i/str"], c["i/attr"]
+    (root / "dataset").mkdir()
+    sio.savemat(str(root / "dataset" / (str(c["i/dataset"]) + ".mat")), mat)
+
+
+@pytest.mark.parametrize("name", golden_cases("data_"))
+def test_load_mat_is_the_reference_split(name, tmp_path, monkeypatch, capsys):
+    """Same .mat, same seed of Python's ``random`` -> the same 12-tuple as utils.py:66-141: adjacency, attributes, labels
+    and every index list element for element (so the two shuffles consume the generator in the reference's order)."""
+    from ggad_b200 import data
+    c = load_case(name)
+    _write_mat(c, tmp_path)
+    monkeypatch.chdir(tmp_path)
+    random.seed(int(c["i/seed"]))
+    out = data.load_mat(str(c["i/dataset"]))
+    assert len(out) == 12
+    adj, feat, ano, all_idx, tr, va, te, ano2, str_a, attr_a, normal, abnormal = out
+    o = c["out"]
+    assert sp.isspmatrix_csr(adj) and sp.isspmatrix_lil(feat)
+    assert np.array_equal(adj.toarray(), o["adj"]) and np.array_equal(feat.toarray(), o["feat"])
+    assert np.array_equal(ano, o["ano_labels"]) and ano2 is ano
+    for got, key in ((all_idx, "all_idx"), (tr, "idx_train"), (va, "idx_val"), (te, "idx_test"),
+                     (normal, "normal_label_idx"), (abnormal, "abnormal_label_idx")):
+        assert isinstance(got, list) and got == o[key].tolist(), key
+    if "str" in o:
+        assert np.array_equal(str_a, o["str"]) and np.array_equal(attr_a, o["attr"])
+    else:
+        assert str_a is None and attr_a is None
+    printed = capsys.readouterr().out
+    assert printed.startswith("Training Counter(") and "Training rate 0.5" in printed
+    # the oracle's restatement of the split (what the GPU tests and smoke() use) agrees with both
+    tr2, va2, te2, normal2, abnormal2 = oracle.load_mat_split(np.asarray(ano), str(c["i/dataset"]), int(c["i/seed"]))
+    assert (tr2, va2, te2, normal2, abnormal2) == (tr, va, te, normal, abnormal)
+    # outlier seeds: 5 % of the labelled normals on Amazon, 15 % elsewhere
+    frac = 0.05 if str(c["i/dataset"]) == "Amazon" else 0.15
+    assert len(abnormal) == int(len(normal) * frac)
+
+
+@pytest.mark.parametrize("name", golden_cases("data_"))
+def test_preprocess_features_and_normalize_adj_bit_exact(name):
+    from ggad_b200 import data
+    c = load_case(name)
+    o = c["out"]
+    dense, (coords, values, shape) = data.preprocess_features(sp.lil_matrix(o["feat"]))
+    assert np.array_equal(np.asarray(dense), o["pre_dense"])                    # same numpy / scipy calls: same bits
+    assert np.array_equal(coords, o["pre_coords"]) and np.array_equal(values, o["pre_values"])
+    assert tuple(shape) == tuple(o["pre_shape"])
+    assert np.all(np.asarray(dense)[5] == 0)                                    # the attribute-less node: inf -> 0
+    a_hat = data.normalize_adj(sp.csr_matrix(o["adj"]))
+    assert np.array_equal(a_hat.toarray(), o["normalize_adj"])
+
+
+def test_load_mat_errors_are_loud(tmp_path, monkeypatch):
+    from ggad_b200 import data
+    monkeypatch.chdir(tmp_path)
+    with pytest.raises(FileNotFoundError):
+        data.load_mat("nope")
+    (tmp_path / "dataset").mkdir()
+    sio.savemat(str(tmp_path / "dataset" / "bad.mat"), {"Label": np.zeros((3, 1)), "Network": sp.eye(3, format="csc")})
+    with pytest.raises(KeyError):
+        data.load_mat("bad")
+
+
+def test_split_does_not_touch_global_random_when_given_its_own_generator():
+    from ggad_b200 import data
+    labels = (np.arange(100) % 7 == 0).astype(int)
+    random.seed(5)
+    before = random.getstate()
+    a = data.semi_supervised_split(labels, "photo", rng=random.Random(1))
+    assert random.getstate() == before
+    b = data.semi_supervised_split(labels, "photo", rng=random.Random(1))
+    assert a == b and len(a[1]) == 30 and len(a[2]) == 10 and len(a[3]) == 60
+    assert sorted(a[0]) == list(range(100)) and set(a[5]) <= set(a[4]) <= set(a[1])
