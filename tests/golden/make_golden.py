@@ -352,9 +352,47 @@ def data_case(ref_utils, name, dataset, n, d, seed, alt_keys, with_kinds):
     print(f"{name}: n={n} train={len(tr)} normal={len(normal)} abnormal={len(abnormal)}")
 
 
+def minibatch_data_case(name, n, d, seed):
+    """src/utils.py (stub for dgl): normalize, sparse_to_adjlist (the later definition, src/utils.py:96-112, wins at
+    import), pos_neg_split on a synthetic graph."""
+    import pickle
+    import tempfile
+    if "dgl" not in sys.modules:
+        try:
+            __import__("dgl")
+        except Exception:
+            sys.modules["dgl"] = types.ModuleType("dgl")
+    spec = importlib.util.spec_from_file_location("ref_src_utils", os.path.join(REF, "src", "utils.py"))
+    u = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(u)
+    rng = np.random.default_rng(seed)
+    a = sp.random(n, n, density=4.0 / n, random_state=rng, data_rvs=lambda k: np.ones(k)).tocsr()   # directed, with isolated nodes
+    x = rng.random((n, d))
+    x[3] = 0
+    x[4] = -0.01 / d                                       # row sum exactly -0.01: 1 / 0 = inf -> 0
+    with tempfile.TemporaryDirectory() as tmp:
+        fn = os.path.join(tmp, "adj")
+        u.sparse_to_adjlist(a, fn)
+        with open(fn, "rb") as f:
+            adj_lists = pickle.load(f)
+    keys = np.array(sorted(adj_lists), dtype=np.int64)
+    lens = np.array([len(adj_lists[k]) for k in keys], dtype=np.int64)
+    flat = np.concatenate([np.array(sorted(adj_lists[k]), dtype=np.int64) for k in keys])
+    nodes = rng.permutation(n)[: n // 2].tolist()
+    nodes[5] = nodes[2]                                    # a duplicated id
+    labels = (rng.random(len(nodes)) < 0.3).astype(np.int64)
+    pos, neg = u.pos_neg_split(nodes, labels)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **{
+        "i/a_data": a.data, "i/a_indices": a.indices, "i/a_indptr": a.indptr, "i/n": n, "i/x": x, "i/nodes": nodes, "i/labels": labels,
+        "o/normalize_dense": np.asarray(u.normalize(x)), "o/normalize_sparse": u.normalize(sp.csr_matrix(x)).toarray(),
+        "o/adj_keys": keys, "o/adj_lens": lens, "o/adj_flat": flat, "o/pos": pos, "o/neg": neg})
+    print(f"{name}: n={n} adjacency-list keys={len(keys)} entries={len(flat)} pos={len(pos)} neg={len(neg)}")
+
+
 def main():
     ref_model, ref_sage = _load_ref()
     ref_utils = _load_ref_utils()
+    minibatch_data_case("mbdata_toy", 500, 9, 4)
     data_case(ref_utils, "data_toy", "toy", 400, 12, 3, alt_keys=False, with_kinds=True)
     data_case(ref_utils, "data_amazon_keys", "Amazon", 900, 9, 11, alt_keys=True, with_kinds=False)
     full_batch_case(ref_model, "fb_sym_binary", "sym_binary", 64, 12, 16, 0, 0.02, 0.01)

@@ -89,3 +89,38 @@ def test_split_does_not_touch_global_random_when_given_its_own_generator():
     b = data.semi_supervised_split(labels, "photo", rng=random.Random(1))
     assert a == b and len(a[1]) == 30 and len(a[2]) == 10 and len(a[3]) == 60
     assert sorted(a[0]) == list(range(100)) and set(a[5]) <= set(a[4]) <= set(a[1])
+
+
+@pytest.mark.parametrize("name", golden_cases("mbdata_"))
+def test_minibatch_data_helpers_match_reference(name, tmp_path):
+    """normalize / sparse_to_adj_lists / pos_neg_split against the reference's src/utils.py run on the same inputs:
+    feature scaling bit for bit (dense and sparse input), the adjacency lists as the same dict of sets (and the same
+    pickle round trip), the positive / negative lists element for element, duplicated id included."""
+    import pickle
+
+    from ggad_b200 import data, graph
+    c = load_case(name)
+    o = c["out"]
+    n = int(c["i/n"])
+    a = sp.csr_matrix((c["i/a_data"], c["i/a_indices"], c["i/a_indptr"]), shape=(n, n))
+    x = c["i/x"]
+    assert np.array_equal(np.asarray(data.normalize(x)), o["normalize_dense"])
+    assert np.array_equal(data.normalize(sp.csr_matrix(x)).toarray(), o["normalize_sparse"])
+    assert np.all(np.asarray(data.normalize(x))[4] == 0)                         # row sum -0.01: 1 / 0 -> 0
+    fn = tmp_path / "adj_list"
+    adj_lists = data.sparse_to_adj_lists(a, str(fn))
+    keys = sorted(adj_lists)
+    assert keys == o["adj_keys"].tolist()
+    ref_sets, pos = {}, 0
+    for k, ln in zip(o["adj_keys"].tolist(), o["adj_lens"].tolist()):
+        ref_sets[k] = set(o["adj_flat"][pos:pos + ln].tolist())
+        pos += ln
+    assert all(adj_lists[k] == ref_sets[k] for k in keys)
+    assert all(type(v) is set and all(type(t) is int for t in v) for v in adj_lists.values())
+    with open(fn, "rb") as f:
+        assert pickle.load(f) == adj_lists
+    # and it is what the aggregators ingest: host CSR with sorted neighbour lists
+    csr = graph.AdjListCSR(adj_lists, n)
+    assert int(csr.rowptr[-1]) == sum(len(v) for v in adj_lists.values())
+    p, ng = data.pos_neg_split(c["i/nodes"].tolist(), c["i/labels"].tolist())
+    assert p == o["pos"].tolist() and ng == o["neg"].tolist()
