@@ -59,3 +59,45 @@ def ggad_loss(emb, logits, emb_con, emb_abnormal, raw_adj, normal_label_idx, abn
     loss_rec = torch.mean(torch.sqrt(torch.sum(diff, 1)))
     loss = 1 * loss_margin + 1 * loss_bce + 1 * loss_rec
     return loss, loss_margin, loss_bce, loss_rec, aff_n, aff_a
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the same local-affinity path as the other full-batch script of the reference uses it (tam.py:113-146)
+# ---------------------------------------------------------------------------------------------------------------
+def _row_col_scale(g: CSRGraph):
+    """rowsum_i / colsum_i of the stored values (0 where the column sum is 0), cached on the graph.  tam.py divides the
+    ROW sums of sim * adj by the COLUMN sums of adj; ops.local_affinity divides by the sums of the rows it reduces."""
+    hit = g.__dict__.get("_row_col_scale")
+    if hit is None:
+        def row_sums(c):
+            ones = torch.ones(c.n_cols, 4, dtype=torch.float32, device=c.device)
+            return ops.gather_reduce(c, ones, use_graph_scales=False)["y"][:, 0]
+        rs, cs = row_sums(g), row_sums(g.T)
+        hit = torch.where(cs != 0, rs / cs, torch.zeros_like(cs))
+        g.__dict__["_row_col_scale"] = hit
+    return hit
+
+
+def inference(feature, adj_matrix):
+    """``tam.inference`` (``tam.py:136-146``): message_i = sum_j adj[i,j] <f^_i, f^_j> / sum_k adj[k,i] for every node,
+    without the N x N similarity matrix.  ``adj_matrix`` is anything ``model.as_graph`` accepts (dense [N,N] tensor, scipy,
+    CSRGraph).  A node with an all-zero feature row contributes 0 (the convention of ``max_message`` and of run.py:177-180;
+    the reference's ``inference`` would return NaN there)."""
+    from .model import as_graph
+    f = feature[0] if feature.dim() == 3 else feature
+    g = as_graph(adj_matrix, f.device)
+    rows = g.__dict__.get("_all_rows")
+    if rows is None:
+        rows = g.__dict__["_all_rows"] = torch.arange(g.n_rows, dtype=torch.int32, device=f.device)
+    # local_affinity(e, R, S)_j = sum_i R[i,j] <e^_i, e^_j> / sum_i R[i,j]; with R = adj^T that is the row-wise sum over adj
+    return ops.local_affinity(f, g.T, rows) * _row_col_scale(g)
+
+
+def max_message(feature, adj_matrix, normal_label_idx):
+    """``tam.max_message`` (``tam.py:113-133``): the messages of ``inference`` min-max normalised over all nodes;
+    returns ``(-sum(message[normal_label_idx]), message)``."""
+    m = inference(feature, adj_matrix)
+    lo, hi = m.min(), m.max()
+    m = (m - lo) / (hi - lo)
+    idx = torch.as_tensor(np.asarray(normal_label_idx, dtype=np.int64), device=m.device)
+    return -m[idx].sum(), m

@@ -389,8 +389,36 @@ def minibatch_data_case(name, n, d, seed):
     print(f"{name}: n={n} adjacency-list keys={len(keys)} entries={len(flat)} pos={len(pos)} neg={len(neg)}")
 
 
+def tam_case(name, kind, n, h, seed):
+    """tam.py is a script; its two affinity functions (tam.py:113-146) are taken out of its source with ``ast`` and run
+    unchanged on a dense adjacency (R = A + I as tam.py feeds them)."""
+    import ast
+    tree = ast.parse(open(os.path.join(REF, "tam.py")).read())
+    ns = {"torch": torch}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("max_message", "inference"):
+            exec(compile(ast.Module([node], []), "tam.py", "exec"), ns)
+    rng = np.random.default_rng(seed)
+    a = sp.csr_matrix(make_graph(kind, n, rng))
+    r = (a + sp.eye(n)).tocsr()
+    torch.manual_seed(seed)
+    feat = torch.randn(n, h)
+    normal = sorted(rng.permutation(n)[: n // 3].tolist())
+    dense = torch.from_numpy(r.toarray().astype(np.float32))
+    f1 = feat.clone().requires_grad_(True)
+    loss, msg = ns["max_message"](f1, dense, normal)
+    loss.backward()
+    inf = ns["inference"](feat, dense)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **{
+        "n": n, "r_data": r.data, "r_indices": r.indices, "r_indptr": r.indptr, "feat": feat.numpy(), "normal": normal,
+        "o/loss": loss.detach().numpy(), "o/message": msg.detach().numpy(), "o/inference": inf.numpy(), "g/feat": f1.grad.numpy()})
+    print(f"{name}: n={n} nnz={r.nnz} loss={float(loss):.5f}")
+
+
 def main():
     ref_model, ref_sage = _load_ref()
+    tam_case("tam_sym", "sym_binary", 120, 16, 0)
+    tam_case("tam_asym_weighted", "asym_weighted", 90, 12, 72)
     ref_utils = _load_ref_utils()
     minibatch_data_case("mbdata_toy", 500, 9, 4)
     data_case(ref_utils, "data_toy", "toy", 400, 12, 3, alt_keys=False, with_kinds=True)

@@ -451,3 +451,26 @@ def test_graphed_minibatch_step_matches_eager():
     for (k, a), (_, b) in zip(m.named_parameters(), ref.named_parameters()):
         if a.requires_grad:
             assert_close(a, b, rtol=2e-4, atol=2e-6, what=f"parameter {k} after 5 graphed batches")
+
+
+@pytest.mark.parametrize("name", golden_cases("tam_"))
+@pytest.mark.parametrize("adj_form", ["csr", "dense"])
+def test_tam_affinity_functions_match_reference(name, adj_form):
+    """losses.max_message / losses.inference (the local-affinity path as tam.py:113-146 calls it: row sums of sim * adj
+    divided by the column sums of adj, min-max normalised) against goldens made by running tam.py's own functions:
+    messages, loss, and the gradient w.r.t. the features; symmetric binary and asymmetric weighted adjacency."""
+    import scipy.sparse as sp
+    from ggad_b200 import graph, losses
+    c = load_case(name)
+    n = int(c["n"])
+    r = sp.csr_matrix((c["r_data"], c["r_indices"], c["r_indptr"]), shape=(n, n))
+    adj = graph.CSRGraph.from_scipy(r.astype(np.float32), "cuda") if adj_form == "csr" \
+        else torch.from_numpy(r.toarray().astype(np.float32)).cuda()
+    feat = torch.from_numpy(c["feat"]).cuda()
+    assert_close(losses.inference(feat, adj), c["out"]["inference"], rtol=1e-4, atol=1e-6, what="tam inference")
+    f = feat.clone().requires_grad_(True)
+    loss, msg = losses.max_message(f, adj, c["normal"].tolist())
+    assert_close(msg, c["out"]["message"], rtol=1e-4, atol=2e-6, what="tam message")
+    assert abs(float(loss.detach()) - float(c["out"]["loss"])) <= 1e-4 * abs(float(c["out"]["loss"]))
+    loss.backward()
+    assert_close(f.grad, c["grads"]["feat"], rtol=5e-4, atol=2e-6, what="tam d loss / d feature")
