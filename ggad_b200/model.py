@@ -151,6 +151,27 @@ class Discriminator(nn.Module):
         self.negsamp_round = negsamp_round
 
 
+class EncoderModel(nn.Module):
+    """The two-layer GCN encoder the reference's other full-batch detectors build from the same ``GCN`` layer
+    (``model_ocgnn.py:109-131``: ``Model(n_in, n_h, activation, negsamp_round, readout)``, ``forward(seq1, adj,
+    sparse=False) -> h_2``; ``model_AEGIS.py:153-156`` stacks the same layer as encoder / decoder).  Same members in the
+    same order, so a reference checkpoint loads with ``strict=True``; both layers run on the gather-reduce path."""
+
+    def __init__(self, n_in, n_h, activation, negsamp_round, readout):
+        super(EncoderModel, self).__init__()
+        self.read_mode = readout
+        self.gcn1 = GCN(n_in, n_h, activation)
+        self.gcn2 = GCN(n_h, n_h, activation)
+        self.act = nn.ReLU()
+        if readout in ('max', 'min', 'avg', 'weighted_sum'):
+            self.read = _Readout(readout)
+        self.disc = Discriminator(n_h, negsamp_round)
+
+    def forward(self, seq1, adj, sparse=False):
+        g = as_graph(adj, seq1.device)
+        return self.gcn2(self.gcn1(seq1, g, sparse), g, sparse)
+
+
 class Model(nn.Module):
     """model.py:108-191.  Unused members (gcn3, fc5, fc6, read, disc) are created in the reference's
     order so seeded initialisation and state_dict keys match."""

@@ -415,8 +415,32 @@ def tam_case(name, kind, n, h, seed):
     print(f"{name}: n={n} nnz={r.nnz} loss={float(loss):.5f}")
 
 
+def encoder_case(name, kind, n, d, h, seed):
+    """model_ocgnn.py (imports only torch): its two-layer GCN encoder ``Model`` on the dense A_hat run.py builds."""
+    spec = importlib.util.spec_from_file_location("ref_model_ocgnn", os.path.join(REF, "model_ocgnn.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    rng = np.random.default_rng(seed)
+    a = sp.csr_matrix(make_graph(kind, n, rng))
+    a_hat = (_ref_normalize_adj(a) + sp.eye(n)).todense()
+    torch.manual_seed(seed)
+    m = ref.Model(d, h, "prelu", 1, "avg")
+    x = torch.randn(1, n, d)
+    out = m(x, torch.FloatTensor(a_hat[np.newaxis]))
+    (out * out).sum().mul(0.5).backward()
+    store = {"n": n, "d": d, "h": h, "a_data": a.data, "a_indices": a.indices, "a_indptr": a.indptr, "x": x.numpy(), "o/h2": out.detach().numpy()}
+    for k, v in m.state_dict().items():
+        store["p/" + k] = v.numpy()
+    for k, p in m.named_parameters():
+        store["g/" + k] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **store)
+    print(f"{name}: n={n} |h2|={float(out.norm()):.4f}")
+
+
 def main():
     ref_model, ref_sage = _load_ref()
+    encoder_case("enc_sym", "sym_binary", 150, 20, 32, 0)
+    encoder_case("enc_asym_weighted", "asym_weighted", 90, 12, 16, 72)
     tam_case("tam_sym", "sym_binary", 120, 16, 0)
     tam_case("tam_asym_weighted", "asym_weighted", 90, 12, 72)
     ref_utils = _load_ref_utils()

@@ -474,3 +474,26 @@ def test_tam_affinity_functions_match_reference(name, adj_form):
     assert abs(float(loss.detach()) - float(c["out"]["loss"])) <= 1e-4 * abs(float(c["out"]["loss"]))
     loss.backward()
     assert_close(f.grad, c["grads"]["feat"], rtol=5e-4, atol=2e-6, what="tam d loss / d feature")
+
+
+@pytest.mark.parametrize("name", golden_cases("enc_"))
+def test_encoder_model_matches_model_ocgnn(name):
+    """model.EncoderModel = the two-layer GCN encoder of model_ocgnn.py:109-131 (the reference's other full-batch
+    detectors reuse the same GCN layer): reference state_dict loads strictly, h_2 and every parameter gradient of
+    0.5 * |h_2|^2 equal the golden produced by the reference class on the dense A_hat."""
+    from ggad_b200 import graph, model
+    c = load_case(name)
+    n, d, h = int(c["n"]), int(c["d"]), int(c["h"])
+    m = model.EncoderModel(d, h, "prelu", 1, "avg")
+    m.load_state_dict(c["params"], strict=True)
+    m = m.cuda()
+    g_hat, _ = graph.full_batch_graphs(case_adjacency(c), "cuda")
+    out = m(torch.from_numpy(c["x"]).cuda(), g_hat)
+    assert out.shape == (1, n, h)
+    assert_close(out.squeeze(0), c["out"]["h2"].squeeze(0), what=f"{name}: h_2")
+    (out * out).sum().mul(0.5).backward()
+    for k, p in m.named_parameters():
+        got = p.grad if p.grad is not None else torch.zeros_like(p)
+        # 0.5 |h_2|^2 gives gradients of magnitude ~60; entries that cancel to ~1e-3 carry the rounding of the large ones
+        atol = max(GRAD_ATOL, 1e-6 * float(np.abs(c["grads"][k].numpy()).max()))
+        assert_close(got, c["grads"][k], rtol=GRAD_RTOL, atol=atol, what=f"{name}: grad {k}")
