@@ -124,3 +124,35 @@ def test_minibatch_data_helpers_match_reference(name, tmp_path):
     assert int(csr.rowptr[-1]) == sum(len(v) for v in adj_lists.values())
     p, ng = data.pos_neg_split(c["i/nodes"].tolist(), c["i/labels"].tolist())
     assert p == o["pos"].tolist() and ng == o["neg"].tolist()
+
+
+def test_data_helpers_properties():
+    """Size-independent properties of the host entry: the adjacency lists are symmetric and cover exactly the stored
+    entries; the split partitions the node ids; feature scaling makes every non-empty row sum to 1 (program A) or to
+    s / (s + 0.01) (program B)."""
+    from hypothesis import given, settings, strategies as st
+
+    from ggad_b200 import data
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.integers(2, 60), st.integers(0, 2 ** 31 - 1))
+    def check(n, seed):
+        rng = np.random.default_rng(seed)
+        a = sp.random(n, n, density=min(1.0, 3.0 / n), random_state=rng, data_rvs=lambda k: np.ones(k)).tocsr()
+        adj = data.sparse_to_adj_lists(a)
+        r, c = a.nonzero()
+        pairs = set(zip(r.tolist(), c.tolist())) | set(zip(c.tolist(), r.tolist()))
+        assert {(u, v) for u, vs in adj.items() for v in vs} == pairs
+        assert all(u in adj[v] for u, vs in adj.items() for v in vs)
+        labels = (rng.random(n) < 0.2).astype(int)
+        all_idx, tr, va, te, normal, abnormal = data.semi_supervised_split(labels, "x", rng=random.Random(seed))
+        assert sorted(tr + va + te) == list(range(n)) == sorted(all_idx)
+        assert all(labels[i] == 0 for i in normal) and set(abnormal) <= set(normal) <= set(tr)
+        x = rng.random((n, 5))
+        x[0] = 0
+        dense = np.asarray(data.preprocess_features(sp.csr_matrix(x))[0])
+        assert np.allclose(dense[1:].sum(1), 1.0) and np.all(dense[0] == 0)
+        s = x.sum(1)
+        assert np.allclose(np.asarray(data.normalize(x)).sum(1), s / (s + 0.01))
+
+    check()
